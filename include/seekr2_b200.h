@@ -1,0 +1,308 @@
+/*
+ * seekr2_b200.h -- C ABI of the B200-native SEEKR2 integrator step (MMVT / Elber Langevin).
+ *
+ * This is the drop-in seam for the per-timestep hot path of the reference plugin
+ * (seekrcentral/seekr2_openmm_plugin).  Every entry point below replaces one piece of the
+ * reference's CUDA-platform kernel implementation and is what a `platforms/b200` OpenMM
+ * KernelImpl (platforms/b200/B200Seekr2Kernels.cpp) binds; the same symbols are bound by
+ * ctypes (seekr2_openmm_plugin_b200/_lib.py) for the standalone harness and the tests.
+ *
+ * Reference interfaces replaced (paths relative to seekr2plugin/ in the reference tree):
+ *   IntegrateMmvtLangevinStepKernel / IntegrateElberLangevinStepKernel
+ *       openmmapi/include/Seekr2Kernels.h:53-110                (initialize / execute)
+ *   CudaIntegrateMmvtLangevinStepKernel::{allocateMemory,initialize,execute}
+ *       platforms/cuda/src/CudaSeekr2Kernels.cpp:82-366
+ *   CudaIntegrateElberLangevinStepKernel::{initialize,execute}
+ *       platforms/cuda/src/CudaSeekr2Kernels.cpp:391-595
+ *   integrate{Mmvt,Elber}LangevinPart1/Part2, mmvtBounce
+ *       platforms/cuda/src/kernels/langevin.cu:7-179
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all pointers named d_* are CUDA device pointers, `stream`
+ *     is a cudaStream_t passed as void*.
+ *   - every function returns an int status (SEEKR2_B200_OK == 0); nothing throws.  The text of
+ *     the last error of the calling thread is available from seekr2_b200_last_error().
+ *   - buffers use the OpenMM CUDA-platform layouts:
+ *       posq            real4 [A][Np]   (x,y,z,q)
+ *       posqCorrection  real4 [A][Np]   low-order position bits, mixed precision only (else NULL)
+ *       velm            mixed4[A][Np]   (vx,vy,vz,1/m); 1/m == 0 marks an immobile particle
+ *       force           int64 [A][3][Np] fixed point, value = F * 2^32, SoA per anchor
+ *       posDelta        mixed4[A][Np]   (two-pass path only)
+ *       random          float4[A][random_anchor_stride], consumed at random_index + atom, .w unused
+ *     A = number of anchors batched in one engine (A == 1 inside OpenMM), Np = padded atom count.
+ *     real/mixed: SINGLE float/float, MIXED float/double, DOUBLE double/double.
+ */
+#ifndef SEEKR2_B200_H_
+#define SEEKR2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEEKR2_B200_ABI_VERSION 1
+
+#define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
+#define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
+#define SEEKR2_B200_MAX_GROUPS 16       /* centroid groups                                        */
+#define SEEKR2_B200_MAX_ELBER 16        /* src + dest milestones of an Elber integrator           */
+
+/* status codes */
+enum {
+    SEEKR2_B200_OK = 0,
+    SEEKR2_B200_ERR_INVALID = 1,        /* bad argument / configuration                           */
+    SEEKR2_B200_ERR_CUDA = 2,           /* a CUDA runtime call failed                             */
+    SEEKR2_B200_ERR_FIRST_STEP = 3,     /* MMVT: system is behind a boundary before the first step
+                                           (CudaSeekr2Kernels.cpp:205-210)                        */
+    SEEKR2_B200_ERR_RING_OVERFLOW = 4,  /* crossing records were dropped: drain more often        */
+    SEEKR2_B200_ERR_IO = 5,             /* crossing / statistics file could not be written        */
+    SEEKR2_B200_ERR_NO_FORCE_GROUP = 6  /* Elber: a milestone's force group has no boundary
+                                           (CudaSeekr2Kernels.cpp:415-436)                        */
+};
+
+/* CudaPrecision of the owning context */
+enum { SEEKR2_B200_SINGLE = 0, SEEKR2_B200_MIXED = 1, SEEKR2_B200_DOUBLE = 2 };
+
+/* which of the reference's two platforms the bounce bookkeeping follows          */
+enum {
+    SEEKR2_B200_VARIANT_CUDA = 0,       /* bounce restores -v(post-kick); N_alpha_beta skips the
+                                           first crossing (CudaSeekr2Kernels.cpp:294-296)         */
+    SEEKR2_B200_VARIANT_REFERENCE = 1   /* bounce restores -v(step start); N_alpha_beta always
+                                           counts (ReferenceSeekr2Kernels.cpp:205-206,290,329-332)*/
+};
+
+/* flags */
+enum {
+    SEEKR2_B200_FLAG_RESTORE_CORRECTION = 1  /* on a bounce also restore posqCorrection.  The
+                                                reference leaves the new correction in place
+                                                (langevin.cu:167-179); default 0 is bit-faithful   */
+};
+
+/* integrator kind */
+enum { SEEKR2_B200_KIND_LANGEVIN = 0, SEEKR2_B200_KIND_MMVT = 1, SEEKR2_B200_KIND_ELBER = 2 };
+
+/* boundary surface types: the typed form of the CustomCentroidBondForce expressions the
+ * reference's examples use.  u is the surface function; the term contributed to
+ * the force-group energy is  bitcode*step(k*u)  (STEP style) or  k*u  (RAW, the older style).   */
+enum {
+    SEEKR2_B200_CV_SPHERE_PAIR = 0,   /* u = distance(g_a,g_b)^2 - threshold^2   (demo3:37)        */
+    SEEKR2_B200_CV_SPHERE_FIXED = 1,  /* u = |c(g_a) - center|^2 - threshold^2   (demo1:59)        */
+    SEEKR2_B200_CV_PLANE = 2          /* u = c(g_a)[axis] - threshold            (demo2:61)        */
+};
+enum { SEEKR2_B200_STYLE_STEP = 0, SEEKR2_B200_STYLE_RAW = 1 };
+
+typedef struct seekr2_b200_boundary {
+    int32_t type;         /* SEEKR2_B200_CV_*                                                      */
+    int32_t style;        /* SEEKR2_B200_STYLE_*                                                   */
+    int32_t group_a;      /* centroid group index                                                  */
+    int32_t group_b;      /* second centroid group (SPHERE_PAIR), else ignored                     */
+    int32_t axis;         /* 0,1,2 (PLANE), else ignored                                           */
+    int32_t force_group;  /* OpenMM force group of the Force carrying the term.  MMVT sums group 1
+                             only (hard-wired mask 2, CudaSeekr2Kernels.cpp:206,248)               */
+    double bitcode;       /* STEP style multiplier (1,2,4,...)                                     */
+    double k;             /* sign selects the side; magnitude matters only for RAW style          */
+    double threshold;     /* radius (nm) or plane position (nm)                                    */
+    double center[3];     /* SPHERE_FIXED centre (nm)                                              */
+} seekr2_b200_boundary;
+
+typedef struct seekr2_b200_config {
+    int32_t abi_version;          /* SEEKR2_B200_ABI_VERSION                                       */
+    int32_t kind;                 /* SEEKR2_B200_KIND_*                                            */
+    int32_t precision;            /* SEEKR2_B200_SINGLE / MIXED / DOUBLE                           */
+    int32_t variant;              /* SEEKR2_B200_VARIANT_*                                         */
+    int32_t flags;                /* SEEKR2_B200_FLAG_*                                            */
+    int32_t device;               /* CUDA device ordinal; -1 = current device                      */
+    int32_t num_anchors;          /* A: independent replicas of the system batched per launch      */
+    int32_t num_atoms;            /* N                                                             */
+    int32_t padded_num_atoms;     /* Np >= N                                                       */
+
+    /* centroid groups, shared by all anchors (same molecular system) */
+    int32_t num_groups;
+    const int32_t* group_offsets; /* [num_groups+1] into group_atoms / group_weights               */
+    const int32_t* group_atoms;   /* atom indices                                                  */
+    const double* group_weights;  /* unnormalised weights (masses); normalised by the library      */
+
+    /* boundary terms: [num_anchors][num_boundaries]; anchors share the structure (type, groups,
+       force_group) and differ only in the numbers (bitcode, k, threshold, center)                 */
+    int32_t num_boundaries;
+    const seekr2_b200_boundary* boundaries;
+
+    /* MMVT: number of addMilestoneGroup() calls = number of bits that are logged and counted
+       (MmvtLangevinIntegrator.cpp:133-136); initial bounceCounter per anchor (may be NULL = 0)    */
+    int32_t num_milestone_groups;
+    const int32_t* bounce_counter0;     /* [num_anchors] or NULL                                   */
+
+    /* Elber: force groups of the source and destination milestones, in add order                  */
+    int32_t num_src;
+    const int32_t* src_groups;          /* [num_src]                                               */
+    int32_t num_dest;
+    const int32_t* dest_groups;         /* [num_dest]                                              */
+    int32_t end_on_src_milestone;
+    const int32_t* crossing_counter0;   /* [num_anchors] or NULL                                   */
+
+    int32_t ring_capacity;        /* crossing records kept per anchor between drains (0 = 4096)    */
+} seekr2_b200_config;
+
+/* device buffers of one step call (borrowed, never owned) */
+typedef struct seekr2_b200_buffers {
+    void* d_posq;
+    void* d_posq_correction;      /* NULL unless MIXED                                             */
+    void* d_velm;
+    const long long* d_force;
+    void* d_pos_delta;            /* two-pass path only; may be NULL for the fused step            */
+    const void* d_random;         /* float4 pool                                                   */
+    int64_t random_anchor_stride; /* float4 elements between consecutive anchors' pools            */
+    void* d_old_velm;             /* VARIANT_REFERENCE two-pass path only: mixed4[A][Np] scratch   */
+} seekr2_b200_buffers;
+
+/* one crossing event, as appended by the device to the per-anchor ring */
+enum {
+    SEEKR2_B200_REC_MMVT = 0,       /* MMVT bounce on bit `index`                                  */
+    SEEKR2_B200_REC_ELBER_SRC = 1,  /* Elber: ended on source milestone `index`                    */
+    SEEKR2_B200_REC_ELBER_DEST = 2, /* Elber: ended on destination milestone `index`               */
+    SEEKR2_B200_REC_ELBER_DEST_STAR = 3 /* same, source never crossed: label gets a '*' suffix     */
+};
+typedef struct seekr2_b200_record {
+    int32_t anchor;
+    int32_t kind;        /* SEEKR2_B200_REC_*                                                      */
+    int32_t index;       /* bit index i (MMVT) or position in the src / dest list (Elber)          */
+    int32_t counter;     /* bounceCounter / crossingCounter written on the line                    */
+    int32_t num_surfaces;/* surfaces crossed in the same step (state is saved only when == 1)      */
+    int32_t reserved;
+    int64_t step;        /* stepCount of the step that crossed                                     */
+    double time;         /* context time written on the line (ps)                                  */
+} seekr2_b200_record;
+
+/* per-anchor integrator state kept on the device (read back by seekr2_b200_get_state) */
+typedef struct seekr2_b200_anchor_state {
+    double time;                 /* cu.getTime()                                                   */
+    double incubation_time;
+    double first_crossing_time;
+    double T_alpha;
+    double Ri_alpha[SEEKR2_B200_MAX_MILESTONES];
+    int64_t step_count;
+    int64_t ring_head;           /* records appended so far (monotonic)                            */
+    int32_t N_alpha_beta[SEEKR2_B200_MAX_MILESTONES];
+    int32_t Nij_alpha[SEEKR2_B200_MAX_MILESTONES * SEEKR2_B200_MAX_MILESTONES];
+    int32_t bounce_counter;
+    int32_t previous_milestone;  /* -1 before the first bounce                                     */
+    int32_t num_bounce_steps;    /* steps that ended in a bounce (diagnostic)                      */
+    int32_t last_value_positive; /* result of the most recent CV evaluation (first-step check)     */
+    /* Elber */
+    int32_t crossing_counter;
+    int32_t crossed_src;
+    int32_t end_simulation;
+    int32_t elber_sampled;       /* bit i set once milestone i has its baseline value              */
+    float elber_values[SEEKR2_B200_MAX_ELBER]; /* src values then dest values                      */
+} seekr2_b200_anchor_state;
+
+typedef struct seekr2_b200_engine* seekr2_b200_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* replaces Cuda*StepKernel::allocateMemory + initialize (CudaSeekr2Kernels.cpp:82-173,391-463):
+   allocates the group slab, per-anchor state and rings; nothing is allocated per step.           */
+int seekr2_b200_create(const seekr2_b200_config* config, seekr2_b200_handle* out);
+int seekr2_b200_destroy(seekr2_b200_handle h);
+const char* seekr2_b200_last_error(void);
+int seekr2_b200_abi_version(void);
+
+/* ---- parameters ---------------------------------------------------------------------------- */
+
+/* replaces the parameter block of execute (CudaSeekr2Kernels.cpp:188-203 / :474-489):
+   vscale = exp(-dt*gamma), fscale = gamma==0 ? dt : (1-vscale)/gamma,
+   noisescale = sqrt(BOLTZ*T*(1-vscale^2)).  Cheap; call whenever T, gamma or dt change.          */
+int seekr2_b200_set_params(seekr2_b200_handle h, double temperature, double friction, double step_size);
+int seekr2_b200_get_params(seekr2_b200_handle h, double out_vscale_fscale_noisescale[3]);
+
+/* ---- state the kernels need besides OpenMM's buffers ---------------------------------------- */
+
+/* (re)gather the boundary-group atoms' state into the engine's double-buffered slab and evaluate
+   the boundary value at the current positions.  Call once before the first fused step and after
+   anything else modified posq/velm (setPositions, setVelocities, reorderAtoms, a barostat).      */
+int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
+
+/* replaces the first-step test (CudaSeekr2Kernels.cpp:205-210): evaluates the MMVT boundary value
+   at the current positions; returns SEEKR2_B200_ERR_FIRST_STEP if any anchor has value > 0 and
+   writes per-anchor flags to out_flags[num_anchors] when non-NULL.  Synchronises the stream.     */
+int seekr2_b200_check_first_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs,
+                                 int32_t* out_flags, void* stream);
+
+/* ---- the step: fused single-pass form (systems without constraints / harness) ---------------- */
+
+/* one full integrator step in ONE launch: Langevin kick + drift (langevin.cu:7-32,65-112), boundary
+   CV evaluation, crossing test, predicated bounce (langevin.cu:167-179), crossing-record append and
+   the statistics / time / step-count epilogue (CudaSeekr2Kernels.cpp:250-365).  kind of the engine
+   selects MMVT, Elber (CudaSeekr2Kernels.cpp:517-594) or plain Langevin.  Asynchronous on `stream`;
+   capturable into a CUDA graph.                                                                    */
+int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index,
+                     void* stream);
+
+/* ---- the step: two-pass form (constraints act on posDelta between the passes) ---------------- */
+
+/* replaces integrate{Mmvt,Elber}LangevinPart1 (langevin.cu:7-59)                                  */
+int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index,
+                     void* stream);
+/* replaces Part2 + calcForcesAndEnergy(false,true,mask) + the host crossing block + mmvtBounce
+   (CudaSeekr2Kernels.cpp:231-365 / :509-594): a one-block-per-anchor decision kernel followed by the
+   streaming finish with the bounce predicated on the device-side decision.                         */
+int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
+
+/* ---- CUDA graph of a sequence of steps -------------------------------------------------------- */
+
+/* begin capturing on `stream`; every seekr2_b200_* step call (and any kernels of the caller's own,
+   e.g. a force provider) issued on that stream until graph_end becomes part of the graph.          */
+int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream);
+int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream);
+int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+
+/* copy the crossing records appended since the previous drain (all anchors, anchor-major, each
+   anchor's records in order) to `out`; *out_n = number written.  Synchronises `stream`.
+   Returns SEEKR2_B200_ERR_RING_OVERFLOW if records were lost.                                      */
+int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records,
+                      int64_t* out_n, void* stream);
+int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anchor_state* out,
+                          void* stream);
+/* Context::setTime / setStepCount analogue (used by reinitialize and by tests)                     */
+int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int64_t step_count,
+                         void* stream);
+
+/* ---- crossing / statistics files (host side of CudaSeekr2Kernels.cpp:158-171,257-345,459-460) -- */
+
+/* write the header iff `path` does not exist (append mode otherwise untouched)                     */
+int seekr2_b200_write_header(int32_t kind, const char* path);
+/* append records of one anchor formatted exactly like the reference:
+   MMVT  "<label>,<counter>,<time %.3f>\n"; Elber "<label>[*],<counter>,<time %g>\n".
+   labels[index] is the milestone group id of bit / list position `index` (src labels first, then
+   dest labels, for Elber).                                                                         */
+int seekr2_b200_append_records(int32_t kind, const char* path, const seekr2_b200_record* recs,
+                               int64_t n, int32_t anchor, const int32_t* labels, int32_t num_labels,
+                               int32_t num_src);
+/* rewrite the MMVT statistics file (CudaSeekr2Kernels.cpp:325-343)                                 */
+int seekr2_b200_write_statistics(const char* path, const seekr2_b200_anchor_state* st,
+                                 const int32_t* labels, int32_t num_labels);
+
+/* ---- harness kernels (stand-ins for what OpenMM supplies; not part of the drop-in path) -------- */
+
+/* harmonic tether force  F = -k (x - x0)  written as int64 fixed point (value * 2^32)              */
+int seekr2_b200_harness_tether_force(int32_t precision, int32_t num_anchors, int32_t num_atoms,
+                                     int32_t padded_num_atoms, const void* d_posq,
+                                     const void* d_posq_correction, const void* d_x0 /* real4 */,
+                                     double k, long long* d_force, void* stream);
+/* harmonic bond force over a bond list (i, j, r0, k), accumulated with 64-bit atomics             */
+int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t padded_num_atoms,
+                                   const void* d_posq, const void* d_posq_correction,
+                                   int32_t num_bonds, const int32_t* d_bond_atoms /* [nb][2] */,
+                                   const double* d_bond_params /* [nb][2] = r0,k */,
+                                   long long* d_force, void* stream);
+/* Philox4x32-10 + Box-Muller Gaussian pool fill (float4, .w = 0)                                   */
+int seekr2_b200_harness_fill_gaussian(void* d_random, int64_t num_float4, uint64_t seed,
+                                      uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEKR2_B200_H_ */

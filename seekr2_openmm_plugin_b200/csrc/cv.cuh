@@ -1,0 +1,234 @@
+// cv.cuh -- milestone boundary evaluation and the crossing bookkeeping that the reference does on
+// the host after a blocking energy readback (CudaSeekr2Kernels.cpp:248-347 and :517-590), done here
+// on the device inside the step kernel.
+//
+// Boundary-value arithmetic contract (shared with the CPU oracle, oracle/seekr2_oracle.c):
+//   P      = (double) posq                      (what OpenMM's force kernels see)
+//   acc_g  = sum_i llrint((w_i * P_i) * 2^40)   int64 fixed point => independent of reduction order
+//   C_g    = (double) acc_g * 2^-40
+//   SPHERE_PAIR / SPHERE_FIXED: u = fma(dz,dz, fma(dy,dy, dx*dx)) - r*r ;  PLANE: u = C[axis] - thr
+//   term = (k*u >= 0 ? bitcode : 0) (STEP) or k*u (RAW); value = in-order double sum of the terms
+#pragma once
+#include "arith.cuh"
+#include "../../include/seekr2_b200.h"
+
+namespace s2 {
+
+using Boundary = seekr2_b200_boundary;
+using AnchorState = seekr2_b200_anchor_state;
+using Record = seekr2_b200_record;
+
+constexpr double kFixedScale = 1099511627776.0;           // 2^40
+constexpr double kFixedInvScale = 1.0 / 1099511627776.0;  // 2^-40
+constexpr unsigned kFullWarp = 0xffffffffu;
+
+// everything a step kernel needs besides the caller's buffers; passed by value
+struct EngineDev {
+    int num_atoms, padded_num_atoms, num_anchors;
+    int num_slots, num_groups, num_boundaries, num_milestone_groups;
+    int variant, flags;
+    int num_src, num_dest, end_on_src;
+    int src_groups[SEEKR2_B200_MAX_ELBER];
+    int dest_groups[SEEKR2_B200_MAX_ELBER];
+    int ring_capacity;
+    const int* slot_atom;        // [num_slots] atom index of each group slot (slots sorted by group)
+    const int* slot_group;       // [num_slots]
+    const double* slot_weight;   // [num_slots] normalised weights
+    const Boundary* boundaries;  // [A][num_boundaries]
+    AnchorState* state;          // [A]
+    Record* ring;                // [A][ring_capacity]
+    void* slab;                  // [2][A][num_slots] SlabEntry<P>
+    int* decision;               // [A] bounce flag of the two-pass path
+};
+
+// shared-memory scratch of the CV phase
+struct CvShared {
+    long long acc[SEEKR2_B200_MAX_GROUPS * 3];
+    double term[SEEKR2_B200_MAX_BOUNDARIES];
+    int force_group[SEEKR2_B200_MAX_BOUNDARIES];
+    int bounce;
+};
+
+__device__ __forceinline__ void cv_clear(CvShared& sh, int num_groups) {
+    if (threadIdx.x < num_groups * 3) sh.acc[threadIdx.x] = 0;
+}
+
+// Adds one slot's weighted position to its group's fixed-point accumulator.  Must be called by all
+// 32 lanes of a warp (invalid lanes pass valid=false).  Slots are sorted by group, so a warp almost
+// always covers a single group: then the three sums are shuffle-reduced and committed with one
+// shared-memory atomic per component; otherwise every lane commits its own.
+__device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, double w, double px,
+                                              double py, double pz) {
+    long long qx = 0, qy = 0, qz = 0;
+    if (valid) {
+        qx = __double2ll_rn(__dmul_rn(__dmul_rn(w, px), kFixedScale));
+        qy = __double2ll_rn(__dmul_rn(__dmul_rn(w, py), kFixedScale));
+        qz = __double2ll_rn(__dmul_rn(__dmul_rn(w, pz), kFixedScale));
+    }
+    const unsigned vmask = __ballot_sync(kFullWarp, valid);
+    if (vmask == 0) return;
+    const int gref = __shfl_sync(kFullWarp, g, __ffs(vmask) - 1);
+    const bool uniform = __all_sync(kFullWarp, !valid || g == gref);
+    if (uniform) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            qx += __shfl_xor_sync(kFullWarp, qx, off);
+            qy += __shfl_xor_sync(kFullWarp, qy, off);
+            qz += __shfl_xor_sync(kFullWarp, qz, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 0], (unsigned long long) qx);
+            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 1], (unsigned long long) qy);
+            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 2], (unsigned long long) qz);
+        }
+    } else if (valid) {
+        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 0], (unsigned long long) qx);
+        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 1], (unsigned long long) qy);
+        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 2], (unsigned long long) qz);
+    }
+}
+
+__device__ __forceinline__ double cv_centroid(const CvShared& sh, int g, int c) {
+    return __dmul_rn(__ll2double_rn(sh.acc[g * 3 + c]), kFixedInvScale);
+}
+
+// one boundary term; evaluated by lane b of warp 0 after the accumulators are complete
+__device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b) {
+    double u;
+    if (b.type == SEEKR2_B200_CV_PLANE) {
+        u = __dsub_rn(cv_centroid(sh, b.group_a, b.axis), b.threshold);
+    } else {
+        double dx, dy, dz;
+        if (b.type == SEEKR2_B200_CV_SPHERE_PAIR) {
+            dx = __dsub_rn(cv_centroid(sh, b.group_a, 0), cv_centroid(sh, b.group_b, 0));
+            dy = __dsub_rn(cv_centroid(sh, b.group_a, 1), cv_centroid(sh, b.group_b, 1));
+            dz = __dsub_rn(cv_centroid(sh, b.group_a, 2), cv_centroid(sh, b.group_b, 2));
+        } else {
+            dx = __dsub_rn(cv_centroid(sh, b.group_a, 0), b.center[0]);
+            dy = __dsub_rn(cv_centroid(sh, b.group_a, 1), b.center[1]);
+            dz = __dsub_rn(cv_centroid(sh, b.group_a, 2), b.center[2]);
+        }
+        const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+        u = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
+    }
+    const double ku = __dmul_rn(b.k, u);
+    if (b.style == SEEKR2_B200_STYLE_RAW) return ku;
+    return ku >= 0.0 ? b.bitcode : 0.0;
+}
+
+// warp 0: lane b evaluates boundary b of this anchor into shared memory
+__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, int anchor) {
+    const int lane = threadIdx.x;
+    if (lane < e.num_boundaries) {
+        const Boundary b = e.boundaries[(size_t) anchor * e.num_boundaries + lane];
+        sh.term[lane] = cv_term(sh, b);
+        sh.force_group[lane] = b.force_group;
+    }
+    __syncwarp();
+}
+
+// energy of one force group == context.calcForcesAndEnergy(false, true, 1 << group); one lane
+__device__ __forceinline__ double cv_group_value(const CvShared& sh, int num_boundaries, int force_group) {
+    double value = 0.0;
+    for (int b = 0; b < num_boundaries; b++)
+        if (sh.force_group[b] == force_group) value = __dadd_rn(value, sh.term[b]);
+    return value;
+}
+
+__device__ __forceinline__ void ring_append(const EngineDev& e, AnchorState& st, int anchor, int kind,
+                                            int index, int counter, int nsurf, double time) {
+    Record r;
+    r.anchor = anchor; r.kind = kind; r.index = index; r.counter = counter;
+    r.num_surfaces = nsurf; r.reserved = 0; r.step = st.step_count; r.time = time;
+    e.ring[(size_t) anchor * e.ring_capacity + (size_t) (st.ring_head % e.ring_capacity)] = r;
+    st.ring_head++;
+}
+
+// The host block of CudaIntegrateMmvtLangevinStepKernel::execute (CudaSeekr2Kernels.cpp:250-347),
+// run by one thread of the anchor's first block.  Returns whether the step bounces.
+__device__ __forceinline__ bool mmvt_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, float value) {
+    st.last_value_positive = value > 0.0f;
+    if (!(value > 0.0f)) return false;
+    int bitcode = (int) value;                                     // :262
+    int num_bounced_surfaces = 0;
+    for (int i = 0; i < e.num_milestone_groups; i++) {              // :264-270
+        if ((bitcode % 2) != 0) num_bounced_surfaces++;
+        bitcode = bitcode >> 1;
+    }
+    bitcode = (int) value;
+    for (int i = 0; i < e.num_milestone_groups; i++) {              // :273-310
+        if ((bitcode % 2) == 0) { bitcode = bitcode >> 1; continue; }
+        bitcode = bitcode >> 1;
+        ring_append(e, st, anchor, SEEKR2_B200_REC_MMVT, i, st.bounce_counter, num_bounced_surfaces, st.time);
+        if (e.variant == SEEKR2_B200_VARIANT_REFERENCE || st.previous_milestone != -1)   // :294-296 / Reference :290
+            st.N_alpha_beta[i] += 1;
+        if (st.previous_milestone != i) {                           // :297-305
+            if (st.previous_milestone != -1) {
+                st.Nij_alpha[st.previous_milestone * SEEKR2_B200_MAX_MILESTONES + i] += 1;
+                st.Ri_alpha[st.previous_milestone] = __dadd_rn(st.Ri_alpha[st.previous_milestone], st.incubation_time);
+            } else {
+                st.first_crossing_time = st.time;
+            }
+            st.incubation_time = 0.0;
+        }
+        st.T_alpha = __dsub_rn(st.time, st.first_crossing_time);    // :306
+        st.previous_milestone = i;
+        st.bounce_counter++;
+    }
+    st.num_bounce_steps++;
+    return true;
+}
+
+// The crossing block of CudaIntegrateElberLangevinStepKernel::execute (CudaSeekr2Kernels.cpp:517-590).
+// elber_values holds the stored source values then destination values; elber_sampled marks which
+// have their baseline (the reference uses -INFINITY as "unsampled").
+__device__ __forceinline__ void elber_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, const CvShared& sh) {
+    if (st.end_simulation) return;                                  // :524
+    const long long head0 = st.ring_head;
+    int num_bounced_surfaces = 0;
+    for (int i = 0; i < e.num_src; i++) {                           // :526-549
+        const float value = (float) cv_group_value(sh, e.num_boundaries, e.src_groups[i]);
+        if (!(st.elber_sampled & (1 << i))) { st.elber_values[i] = value; st.elber_sampled |= 1 << i; }
+        const float oldvalue = st.elber_values[i];
+        const bool time_ok = e.variant == SEEKR2_B200_VARIANT_REFERENCE ? true : (st.time != 0.0);   // :533 / Reference :472
+        if (((value - oldvalue) != 0.0f) && time_ok) {
+            if (e.end_on_src) {
+                st.end_simulation = 1;
+                num_bounced_surfaces++;
+                ring_append(e, st, anchor, SEEKR2_B200_REC_ELBER_SRC, i, st.crossing_counter, 0, st.time);
+            } else {
+                st.crossed_src = 1;
+                st.time = 0.0;                                      // context.setTime(0.0) :545
+                st.elber_values[i] = value;
+            }
+        }
+    }
+    for (int i = 0; i < e.num_dest; i++) {                          // :551-572
+        const int j = e.num_src + i;
+        const float value = (float) cv_group_value(sh, e.num_boundaries, e.dest_groups[i]);
+        if (!(st.elber_sampled & (1 << j))) { st.elber_values[j] = value; st.elber_sampled |= 1 << j; }
+        const float oldvalue = st.elber_values[j];
+        const bool time_ok = e.variant == SEEKR2_B200_VARIANT_REFERENCE ? true : (st.time != 0.0);   // :558 / Reference :498
+        if (((value - oldvalue) != 0.0f) && time_ok) {
+            st.end_simulation = 1;
+            num_bounced_surfaces++;
+            const bool star = !(st.crossed_src || e.end_on_src);    // :564-568
+            ring_append(e, st, anchor, star ? SEEKR2_B200_REC_ELBER_DEST_STAR : SEEKR2_B200_REC_ELBER_DEST, i,
+                        st.crossing_counter, 0, st.time);
+        }
+    }
+    if (st.end_simulation) {                                        // :573-589
+        for (long long h = head0; h < st.ring_head; h++)
+            e.ring[(size_t) anchor * e.ring_capacity + (size_t) (h % e.ring_capacity)].num_surfaces = num_bounced_surfaces;
+        st.crossing_counter++;
+    }
+}
+
+// step epilogue: CudaSeekr2Kernels.cpp:362-364 (MMVT) / :592-593 (Elber)
+__device__ __forceinline__ void advance_clock(AnchorState& st, double dt, bool mmvt) {
+    st.time = __dadd_rn(st.time, dt);
+    st.step_count++;
+    if (mmvt) st.incubation_time = __dadd_rn(st.incubation_time, dt);
+}
+
+}  // namespace s2

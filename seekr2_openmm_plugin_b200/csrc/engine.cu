@@ -1,0 +1,596 @@
+// engine.cu -- host side of the C ABI declared in include/seekr2_b200.h.
+//
+// This is the B200 counterpart of the host code of the reference's CUDA platform kernels
+// (seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.cpp:63-599): it owns the per-engine device
+// state (group slab, per-anchor integrator state, crossing rings), turns T / gamma / dt into the
+// kernel parameters, launches the step kernels on the caller's stream and formats the crossing and
+// statistics files.  Unlike the reference there is no per-step host work besides the launch itself:
+// no energy readback, no host branch for the bounce, no file I/O inside the step.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace s2;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return fail(SEEKR2_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                        cudaGetErrorString(err__), __FILE__, __LINE__);                        \
+    } while (0)
+
+// OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
+// the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
+constexpr double kBoltzmann = 1.380649e-23;
+constexpr double kAvogadro = 6.02214076e23;
+constexpr double kBoltz = (kBoltzmann * kAvogadro) / 1000.0;
+
+size_t slab_entry_size(int precision) {
+    switch (precision) {
+    case SINGLE: return sizeof(SlabEntry<SINGLE>);
+    case MIXED: return sizeof(SlabEntry<MIXED>);
+    default: return sizeof(SlabEntry<DOUBLE>);
+    }
+}
+
+}  // namespace
+
+struct seekr2_b200_engine {
+    seekr2_b200_config cfg{};
+    EngineDev dev{};
+    int device = 0;
+    double params[3] = {0, 0, 0};   // vscale, fscale, noisescale
+    double step_size = 0.0;
+    bool params_set = false;
+    int parity = 0;                 // slab half holding the current group state
+    bool slab_valid = false;
+    // device allocations
+    int* d_slot_atom = nullptr;
+    int* d_slot_group = nullptr;
+    double* d_slot_weight = nullptr;
+    Boundary* d_boundaries = nullptr;
+    AnchorState* d_state = nullptr;
+    Record* d_ring = nullptr;
+    void* d_slab = nullptr;
+    int* d_decision = nullptr;
+    // host mirrors for drain
+    AnchorState* h_state = nullptr;           // pinned [A]
+    std::vector<long long> ring_tail;         // records already drained, per anchor
+    // graph capture
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool capturing = false;
+    int capture_parity0 = 0;
+    int capture_steps = 0;
+    int graph_steps = 0;
+};
+
+namespace {
+
+template <int P> Bufs<P> typed_bufs(const seekr2_b200_buffers* b) {
+    Bufs<P> t;
+    t.posq = (typename Prec<P>::real4*) b->d_posq;
+    t.corr = (typename Prec<P>::real4*) b->d_posq_correction;
+    t.velm = (typename Prec<P>::mixed4*) b->d_velm;
+    t.force = b->d_force;
+    t.pos_delta = (typename Prec<P>::mixed4*) b->d_pos_delta;
+    t.random = (const float4*) b->d_random;
+    t.random_anchor_stride = b->random_anchor_stride;
+    t.old_velm = (typename Prec<P>::mixed4*) b->d_old_velm;
+    return t;
+}
+
+// kernel parameters in the precision the reference kernels compute in (langevin.cu:13-16,71)
+template <int P> StepParams<P> step_params(const seekr2_b200_engine* h) {
+    using M = typename Prec<P>::mixed;
+    StepParams<P> p;
+    p.vscale = (M) h->params[0];
+    p.fs = (M) h->params[1] / (M) 4294967296.0;
+    p.noisescale = (M) h->params[2];
+    p.dt = (M) h->step_size;
+    p.inv_dt = 1.0 / (double) p.dt;
+    return p;
+}
+
+dim3 atom_grid(const seekr2_b200_engine* h) {
+    return dim3((unsigned) ((h->cfg.num_atoms + kThreads - 1) / kThreads), (unsigned) h->cfg.num_anchors, 1);
+}
+
+int check_bufs(const seekr2_b200_engine* h, const seekr2_b200_buffers* b, bool need_random, bool need_delta) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    if (!b || !b->d_posq || !b->d_velm || !b->d_force) return fail(SEEKR2_B200_ERR_INVALID, "posq, velm and force buffers are required");
+    if (h->cfg.precision == MIXED && !b->d_posq_correction) return fail(SEEKR2_B200_ERR_INVALID, "mixed precision needs posqCorrection");
+    if (need_random && !b->d_random) return fail(SEEKR2_B200_ERR_INVALID, "random pool is required");
+    if (need_delta && !b->d_pos_delta) return fail(SEEKR2_B200_ERR_INVALID, "posDelta is required for the two-pass path");
+    if (!h->params_set) return fail(SEEKR2_B200_ERR_INVALID, "seekr2_b200_set_params has not been called");
+    return SEEKR2_B200_OK;
+}
+
+template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
+    if (h->dev.num_slots > 0) {
+        dim3 grid((unsigned) ((h->dev.num_slots + kThreads - 1) / kThreads), (unsigned) h->cfg.num_anchors, 1);
+        gather_groups_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->parity);
+    }
+    decide_kernel<P, SEEKR2_B200_KIND_MMVT, 1><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+template <int P, int KIND> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+    fused_step_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+template <int P> int launch_fused_kind(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+    switch (h->cfg.kind) {
+    case SEEKR2_B200_KIND_MMVT: return launch_fused<P, SEEKR2_B200_KIND_MMVT>(h, b, ri, s);
+    case SEEKR2_B200_KIND_ELBER: return launch_fused<P, SEEKR2_B200_KIND_ELBER>(h, b, ri, s);
+    default: return launch_fused<P, SEEKR2_B200_KIND_LANGEVIN>(h, b, ri, s);
+    }
+}
+
+template <int P> int launch_kick(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+    kick_kernel<P><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), ri);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+template <int P, int KIND> int launch_finish(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
+    decide_kernel<P, KIND, 0><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
+    finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+template <int P> int launch_finish_kind(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
+    switch (h->cfg.kind) {
+    case SEEKR2_B200_KIND_MMVT: return launch_finish<P, SEEKR2_B200_KIND_MMVT>(h, b, s);
+    case SEEKR2_B200_KIND_ELBER: return launch_finish<P, SEEKR2_B200_KIND_ELBER>(h, b, s);
+    default: return launch_finish<P, SEEKR2_B200_KIND_LANGEVIN>(h, b, s);
+    }
+}
+
+#define DISPATCH_PRECISION(h, expr_single, expr_mixed, expr_double) \
+    ((h)->cfg.precision == SINGLE ? (expr_single) : (h)->cfg.precision == MIXED ? (expr_mixed) : (expr_double))
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int seekr2_b200_abi_version(void) { return SEEKR2_B200_ABI_VERSION; }
+const char* seekr2_b200_last_error(void) { return g_last_error.c_str(); }
+
+int seekr2_b200_destroy(seekr2_b200_handle h) {
+    if (!h) return SEEKR2_B200_OK;
+    DeviceGuard guard(h->device);   // the reference's destructors call cu.setAsCurrent() first (:74-80)
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    cudaFree(h->d_slot_atom); cudaFree(h->d_slot_group); cudaFree(h->d_slot_weight);
+    cudaFree(h->d_boundaries); cudaFree(h->d_state); cudaFree(h->d_ring); cudaFree(h->d_slab);
+    cudaFree(h->d_decision);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    delete h;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
+    if (!cfg || !out) return fail(SEEKR2_B200_ERR_INVALID, "null config or output handle");
+    *out = nullptr;
+    if (cfg->abi_version != SEEKR2_B200_ABI_VERSION) return fail(SEEKR2_B200_ERR_INVALID, "ABI version mismatch: header %d, caller %d", SEEKR2_B200_ABI_VERSION, cfg->abi_version);
+    if (cfg->precision < SINGLE || cfg->precision > DOUBLE) return fail(SEEKR2_B200_ERR_INVALID, "bad precision %d", cfg->precision);
+    if (cfg->kind < SEEKR2_B200_KIND_LANGEVIN || cfg->kind > SEEKR2_B200_KIND_ELBER) return fail(SEEKR2_B200_ERR_INVALID, "bad integrator kind %d", cfg->kind);
+    if (cfg->variant != SEEKR2_B200_VARIANT_CUDA && cfg->variant != SEEKR2_B200_VARIANT_REFERENCE) return fail(SEEKR2_B200_ERR_INVALID, "bad variant %d", cfg->variant);
+    if (cfg->num_anchors < 1 || cfg->num_anchors > 65535) return fail(SEEKR2_B200_ERR_INVALID, "num_anchors must be in [1, 65535]");
+    if (cfg->num_atoms < 1 || cfg->padded_num_atoms < cfg->num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "bad atom counts %d / %d", cfg->num_atoms, cfg->padded_num_atoms);
+    if (cfg->num_groups < 0 || cfg->num_groups > SEEKR2_B200_MAX_GROUPS) return fail(SEEKR2_B200_ERR_INVALID, "at most %d centroid groups", SEEKR2_B200_MAX_GROUPS);
+    if (cfg->num_boundaries < 0 || cfg->num_boundaries > SEEKR2_B200_MAX_BOUNDARIES) return fail(SEEKR2_B200_ERR_INVALID, "at most %d boundaries", SEEKR2_B200_MAX_BOUNDARIES);
+    if (cfg->num_milestone_groups < 0 || cfg->num_milestone_groups > SEEKR2_B200_MAX_MILESTONES) return fail(SEEKR2_B200_ERR_INVALID, "at most %d milestone groups", SEEKR2_B200_MAX_MILESTONES);
+    if (cfg->num_src < 0 || cfg->num_dest < 0 || cfg->num_src + cfg->num_dest > SEEKR2_B200_MAX_ELBER) return fail(SEEKR2_B200_ERR_INVALID, "at most %d Elber milestones", SEEKR2_B200_MAX_ELBER);
+    if (cfg->num_groups > 0 && (!cfg->group_offsets || !cfg->group_atoms || !cfg->group_weights)) return fail(SEEKR2_B200_ERR_INVALID, "group arrays missing");
+    if (cfg->num_boundaries > 0 && !cfg->boundaries) return fail(SEEKR2_B200_ERR_INVALID, "boundary array missing");
+
+    const int num_slots = cfg->num_groups > 0 ? cfg->group_offsets[cfg->num_groups] : 0;
+    std::vector<int> slot_atom(num_slots), slot_group(num_slots);
+    std::vector<double> slot_weight(num_slots);
+    for (int g = 0; g < cfg->num_groups; g++) {
+        const int lo = cfg->group_offsets[g], hi = cfg->group_offsets[g + 1];
+        if (hi <= lo) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d is empty", g);
+        // OpenMM normalises the weights of a centroid group so that they sum to one
+        double sum = 0.0;
+        for (int j = lo; j < hi; j++) sum += cfg->group_weights[j];
+        if (!(sum > 0.0)) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d has non-positive total weight", g);
+        for (int j = lo; j < hi; j++) {
+            if (cfg->group_atoms[j] < 0 || cfg->group_atoms[j] >= cfg->num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "group %d references atom %d outside [0,%d)", g, cfg->group_atoms[j], cfg->num_atoms);
+            slot_atom[j] = cfg->group_atoms[j];
+            slot_group[j] = g;
+            slot_weight[j] = cfg->group_weights[j] / sum;
+        }
+    }
+    for (int a = 0; a < cfg->num_anchors; a++)
+        for (int i = 0; i < cfg->num_boundaries; i++) {
+            const seekr2_b200_boundary& bd = cfg->boundaries[(size_t) a * cfg->num_boundaries + i];
+            if (bd.type < SEEKR2_B200_CV_SPHERE_PAIR || bd.type > SEEKR2_B200_CV_PLANE) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: unknown type %d", i, bd.type);
+            if (bd.group_a < 0 || bd.group_a >= cfg->num_groups) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group_a %d", i, bd.group_a);
+            if (bd.type == SEEKR2_B200_CV_SPHERE_PAIR && (bd.group_b < 0 || bd.group_b >= cfg->num_groups)) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group_b %d", i, bd.group_b);
+            if (bd.type == SEEKR2_B200_CV_PLANE && (bd.axis < 0 || bd.axis > 2)) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad axis %d", i, bd.axis);
+        }
+    if (cfg->kind == SEEKR2_B200_KIND_ELBER) {
+        // every milestone's force group must carry a Force (CudaSeekr2Kernels.cpp:415-436)
+        for (int pass = 0; pass < 2; pass++) {
+            const int n = pass == 0 ? cfg->num_src : cfg->num_dest;
+            const int32_t* groups = pass == 0 ? cfg->src_groups : cfg->dest_groups;
+            if (n > 0 && !groups) return fail(SEEKR2_B200_ERR_INVALID, "Elber milestone group array missing");
+            for (int i = 0; i < n; i++) {
+                bool found = false;
+                for (int bnd = 0; bnd < cfg->num_boundaries; bnd++) found |= cfg->boundaries[bnd].force_group == groups[i];
+                if (!found) return fail(SEEKR2_B200_ERR_NO_FORCE_GROUP, "System contains no force groups used to detect Elber boundary crossings. Check for mismatches between force group assignments and the groups added to the Elber integrator.");
+            }
+        }
+    }
+
+    seekr2_b200_engine* h = new (std::nothrow) seekr2_b200_engine();
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->cfg.group_offsets = nullptr; h->cfg.group_atoms = nullptr; h->cfg.group_weights = nullptr;
+    h->cfg.boundaries = nullptr; h->cfg.bounce_counter0 = nullptr; h->cfg.src_groups = nullptr;
+    h->cfg.dest_groups = nullptr; h->cfg.crossing_counter0 = nullptr;
+    if (h->cfg.ring_capacity <= 0) h->cfg.ring_capacity = 4096;
+    if (cfg->device >= 0) h->device = cfg->device; else cudaGetDevice(&h->device);
+    DeviceGuard guard(h->device);
+
+    const int A = cfg->num_anchors;
+    EngineDev& d = h->dev;
+    d.num_atoms = cfg->num_atoms; d.padded_num_atoms = cfg->padded_num_atoms; d.num_anchors = A;
+    d.num_slots = num_slots; d.num_groups = cfg->num_groups; d.num_boundaries = cfg->num_boundaries;
+    d.num_milestone_groups = cfg->num_milestone_groups;
+    d.variant = cfg->variant; d.flags = cfg->flags;
+    d.num_src = cfg->num_src; d.num_dest = cfg->num_dest; d.end_on_src = cfg->end_on_src_milestone ? 1 : 0;
+    for (int i = 0; i < cfg->num_src; i++) d.src_groups[i] = cfg->src_groups[i];
+    for (int i = 0; i < cfg->num_dest; i++) d.dest_groups[i] = cfg->dest_groups[i];
+    d.ring_capacity = h->cfg.ring_capacity;
+
+    auto bail = [&](int code) { seekr2_b200_destroy(h); return code; };
+#define CREATE_TRY(call)                                                                            \
+    do {                                                                                            \
+        cudaError_t err__ = (call);                                                                 \
+        if (err__ != cudaSuccess) {                                                                 \
+            fail(SEEKR2_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__));          \
+            return bail(SEEKR2_B200_ERR_CUDA);                                                      \
+        }                                                                                           \
+    } while (0)
+
+    if (num_slots > 0) {
+        CREATE_TRY(cudaMalloc(&h->d_slot_atom, sizeof(int) * num_slots));
+        CREATE_TRY(cudaMalloc(&h->d_slot_group, sizeof(int) * num_slots));
+        CREATE_TRY(cudaMalloc(&h->d_slot_weight, sizeof(double) * num_slots));
+        CREATE_TRY(cudaMemcpy(h->d_slot_atom, slot_atom.data(), sizeof(int) * num_slots, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_slot_group, slot_group.data(), sizeof(int) * num_slots, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_slot_weight, slot_weight.data(), sizeof(double) * num_slots, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&h->d_slab, slab_entry_size(cfg->precision) * 2 * (size_t) A * num_slots));
+        CREATE_TRY(cudaMemset(h->d_slab, 0, slab_entry_size(cfg->precision) * 2 * (size_t) A * num_slots));
+    }
+    if (cfg->num_boundaries > 0) {
+        const size_t nb = (size_t) A * cfg->num_boundaries;
+        CREATE_TRY(cudaMalloc(&h->d_boundaries, sizeof(Boundary) * nb));
+        CREATE_TRY(cudaMemcpy(h->d_boundaries, cfg->boundaries, sizeof(Boundary) * nb, cudaMemcpyHostToDevice));
+    }
+    CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
+    CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
+    CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * A));
+    CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * A));
+    CREATE_TRY(cudaHostAlloc(&h->h_state, sizeof(AnchorState) * A, cudaHostAllocDefault));
+    // initialize(): zero statistics, seed counters (CudaSeekr2Kernels.cpp:118-133,151-154,403-404)
+    memset(h->h_state, 0, sizeof(AnchorState) * A);
+    for (int a = 0; a < A; a++) {
+        h->h_state[a].previous_milestone = -1;
+        h->h_state[a].bounce_counter = cfg->bounce_counter0 ? cfg->bounce_counter0[a] : 0;
+        h->h_state[a].crossing_counter = cfg->crossing_counter0 ? cfg->crossing_counter0[a] : 0;
+    }
+    CREATE_TRY(cudaMemcpy(h->d_state, h->h_state, sizeof(AnchorState) * A, cudaMemcpyHostToDevice));
+    h->ring_tail.assign(A, 0);
+
+    d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
+    d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
+    d.decision = h->d_decision;
+    *out = h;
+    return SEEKR2_B200_OK;
+#undef CREATE_TRY
+}
+
+int seekr2_b200_set_params(seekr2_b200_handle h, double temperature, double friction, double step_size) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "parameters cannot change inside a graph capture");
+    // CudaSeekr2Kernels.cpp:191-194
+    const double kT = kBoltz * temperature;
+    const double vscale = exp(-step_size * friction);
+    const double fscale = (friction == 0 ? step_size : (1 - vscale) / friction);
+    const double noisescale = sqrt(kT * (1 - vscale * vscale));
+    h->params[0] = vscale; h->params[1] = fscale; h->params[2] = noisescale;
+    h->step_size = step_size;
+    h->params_set = true;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_get_params(seekr2_b200_handle h, double out[3]) {
+    if (!h || !out) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    memcpy(out, h->params, sizeof(double) * 3);
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream) {
+    if (int rc = check_bufs(h, bufs, false, false)) return rc;
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "sync_groups cannot be captured");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    int rc = DISPATCH_PRECISION(h, launch_gather<SINGLE>(h, bufs, s), launch_gather<MIXED>(h, bufs, s), launch_gather<DOUBLE>(h, bufs, s));
+    if (rc == SEEKR2_B200_OK) h->slab_valid = true;
+    return rc;
+}
+
+int seekr2_b200_check_first_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, int32_t* out_flags, void* stream) {
+    if (int rc = seekr2_b200_sync_groups(h, bufs, stream)) return rc;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    const int A = h->cfg.num_anchors;
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(AnchorState) * A, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    bool any = false;
+    for (int a = 0; a < A; a++) {
+        const int flag = h->h_state[a].last_value_positive;
+        if (out_flags) out_flags[a] = flag;
+        any |= flag != 0;
+    }
+    if (any && h->cfg.kind == SEEKR2_B200_KIND_MMVT)
+        return fail(SEEKR2_B200_ERR_FIRST_STEP, "MMVT simulation bouncing on first step: the system will be trapped behind a boundary. Check and revise MMVT boundary definitions and/or atomic positions.");
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index, void* stream) {
+    if (int rc = check_bufs(h, bufs, true, false)) return rc;
+    if (h->cfg.kind != SEEKR2_B200_KIND_LANGEVIN && h->dev.num_slots > 0 && !h->slab_valid)
+        return fail(SEEKR2_B200_ERR_INVALID, "seekr2_b200_sync_groups must be called before the first fused step");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    int rc = DISPATCH_PRECISION(h, launch_fused_kind<SINGLE>(h, bufs, random_index, s),
+                                launch_fused_kind<MIXED>(h, bufs, random_index, s),
+                                launch_fused_kind<DOUBLE>(h, bufs, random_index, s));
+    if (rc != SEEKR2_B200_OK) return rc;
+    if (h->cfg.kind != SEEKR2_B200_KIND_LANGEVIN) h->parity ^= 1;
+    if (h->capturing) h->capture_steps++;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index, void* stream) {
+    if (int rc = check_bufs(h, bufs, true, true)) return rc;
+    if (h->cfg.variant == SEEKR2_B200_VARIANT_REFERENCE && h->cfg.kind == SEEKR2_B200_KIND_MMVT && !bufs->d_old_velm)
+        return fail(SEEKR2_B200_ERR_INVALID, "VARIANT_REFERENCE two-pass MMVT needs d_old_velm");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    return DISPATCH_PRECISION(h, launch_kick<SINGLE>(h, bufs, random_index, s), launch_kick<MIXED>(h, bufs, random_index, s),
+                              launch_kick<DOUBLE>(h, bufs, random_index, s));
+}
+
+int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream) {
+    if (int rc = check_bufs(h, bufs, false, true)) return rc;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    h->slab_valid = false;   // the two-pass path does not maintain the slab
+    return DISPATCH_PRECISION(h, launch_finish_kind<SINGLE>(h, bufs, s), launch_finish_kind<MIXED>(h, bufs, s),
+                              launch_finish_kind<DOUBLE>(h, bufs, s));
+}
+
+int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "already capturing");
+    DeviceGuard guard(h->device);
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    CUDA_TRY(cudaStreamBeginCapture((cudaStream_t) stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    h->capture_parity0 = h->parity;
+    h->capture_steps = 0;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream) {
+    if (!h || !h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "not capturing");
+    DeviceGuard guard(h->device);
+    h->capturing = false;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(cudaStreamEndCapture((cudaStream_t) stream, &g));
+    h->graph = g;
+    h->parity = h->capture_parity0;      // the captured steps have not run yet
+    h->graph_steps = h->capture_steps;
+    if (h->cfg.kind != SEEKR2_B200_KIND_LANGEVIN && (h->graph_steps & 1))
+        return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain an even number of fused steps (the slab parity is baked into each launch); got %d", h->graph_steps);
+    CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream) {
+    if (!h || !h->graph_exec) return fail(SEEKR2_B200_ERR_INVALID, "no instantiated step graph");
+    if (h->parity != h->capture_parity0) return fail(SEEKR2_B200_ERR_INVALID, "slab parity differs from the one the graph was captured with");
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaGraphLaunch(h->graph_exec, (cudaStream_t) stream));
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n, void* stream) {
+    if (!h || !out_n) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "drain cannot be captured");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    const int A = h->cfg.num_anchors;
+    const int cap = h->dev.ring_capacity;
+    *out_n = 0;
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(AnchorState) * A, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    bool overflow = false;
+    int64_t n = 0;
+    for (int a = 0; a < A; a++) {
+        long long head = h->h_state[a].ring_head, tail = h->ring_tail[a];
+        if (head - tail > cap) { overflow = true; tail = head - cap; }
+        while (tail < head) {
+            const long long pos = tail % cap;
+            long long chunk = head - tail;
+            if (chunk > cap - pos) chunk = cap - pos;
+            if (n + chunk > max_records) { chunk = max_records - n; }
+            if (chunk <= 0) break;
+            if (!out) return fail(SEEKR2_B200_ERR_INVALID, "null record buffer");
+            CUDA_TRY(cudaMemcpyAsync(out + n, h->d_ring + (size_t) a * cap + pos, sizeof(Record) * chunk, cudaMemcpyDeviceToHost, s));
+            n += chunk; tail += chunk;
+        }
+        h->ring_tail[a] = tail;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *out_n = n;
+    if (overflow) return fail(SEEKR2_B200_ERR_RING_OVERFLOW, "crossing ring overflowed: records were lost; drain more often or raise ring_capacity");
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anchor_state* out, void* stream) {
+    if (!h || !out || anchor < 0 || anchor >= h->cfg.num_anchors) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_state + anchor, sizeof(AnchorState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int64_t step_count, void* stream) {
+    if (!h || anchor < 0 || anchor >= h->cfg.num_anchors) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaMemcpy(&h->d_state[anchor].time, &time, sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(&h->d_state[anchor].step_count, &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
+    return SEEKR2_B200_OK;
+}
+
+// ---- files ------------------------------------------------------------------------------------
+
+int seekr2_b200_write_header(int32_t kind, const char* path) {
+    if (!path) return fail(SEEKR2_B200_ERR_INVALID, "null path");
+    // "see whether the file already exists" (CudaSeekr2Kernels.cpp:158-171, :447-462)
+    if (FILE* probe = fopen(path, "r")) { fclose(probe); return SEEKR2_B200_OK; }
+    FILE* f = fopen(path, "a");
+    if (!f) return fail(SEEKR2_B200_ERR_IO, "cannot open %s", path);
+    if (kind == SEEKR2_B200_KIND_ELBER) {
+        fputs("#\"Crossed boundary ID\",\"crossing counter\",\"total time (ps)\"\n", f);
+        fputs("# An asterisk(*) indicates that source milestone was never crossed - asterisked statistics are invalid and should be excluded.\n", f);
+    } else {
+        fputs("#\"Bounced boundary ID\",\"bounce index\",\"total time (ps)\"\n", f);
+    }
+    fclose(f);
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_append_records(int32_t kind, const char* path, const seekr2_b200_record* recs, int64_t n,
+                               int32_t anchor, const int32_t* labels, int32_t num_labels, int32_t num_src) {
+    if (!path || (n > 0 && (!recs || !labels))) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    (void) kind;
+    FILE* f = fopen(path, "a");                       // std::ios_base::app (:258, :539, :563)
+    if (!f) return fail(SEEKR2_B200_ERR_IO, "cannot open %s", path);
+    for (int64_t r = 0; r < n; r++) {
+        const seekr2_b200_record& rec = recs[r];
+        if (rec.anchor != anchor) continue;
+        const int li = (rec.kind == SEEKR2_B200_REC_ELBER_DEST || rec.kind == SEEKR2_B200_REC_ELBER_DEST_STAR) ? num_src + rec.index : rec.index;
+        if (li < 0 || li >= num_labels) { fclose(f); return fail(SEEKR2_B200_ERR_INVALID, "record index %d has no label", li); }
+        switch (rec.kind) {
+        case SEEKR2_B200_REC_MMVT:   // fixed, precision(3) (:259-260,281)
+            fprintf(f, "%d,%d,%.3f\n", labels[li], rec.counter, rec.time); break;
+        case SEEKR2_B200_REC_ELBER_DEST_STAR:   // default ostream formatting == %g (:567)
+            fprintf(f, "%d*,%d,%g\n", labels[li], rec.counter, rec.time); break;
+        default:
+            fprintf(f, "%d,%d,%g\n", labels[li], rec.counter, rec.time); break;
+        }
+    }
+    fclose(f);
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_write_statistics(const char* path, const seekr2_b200_anchor_state* st, const int32_t* labels, int32_t num_labels) {
+    if (!path || !st || (num_labels > 0 && !labels) || num_labels > SEEKR2_B200_MAX_MILESTONES) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    FILE* f = fopen(path, "w");                       // ios_base::trunc (:326)
+    if (!f) return fail(SEEKR2_B200_ERR_IO, "cannot open %s", path);
+    for (int i = 0; i < num_labels; i++) fprintf(f, "N_alpha_%d: %d\n", labels[i], st->N_alpha_beta[i]);
+    for (int i = 0; i < num_labels; i++)
+        for (int j = 0; j < num_labels; j++)
+            fprintf(f, "N_%d_%d_alpha: %d\n", labels[i], labels[j], st->Nij_alpha[i * SEEKR2_B200_MAX_MILESTONES + j]);
+    for (int i = 0; i < num_labels; i++) fprintf(f, "R_%d_alpha: %.3f\n", labels[i], st->Ri_alpha[i]);
+    fprintf(f, "T_alpha: %.3f\n", st->T_alpha);
+    fclose(f);
+    return SEEKR2_B200_OK;
+}
+
+// ---- harness ------------------------------------------------------------------------------------
+
+int seekr2_b200_harness_tether_force(int32_t precision, int32_t num_anchors, int32_t num_atoms, int32_t padded,
+                                     const void* d_posq, const void* d_posq_correction, const void* d_x0, double k,
+                                     long long* d_force, void* stream) {
+    (void) d_posq_correction;   // forces see posq only, as OpenMM's force kernels do
+    if (!d_posq || !d_x0 || !d_force) return fail(SEEKR2_B200_ERR_INVALID, "null buffer");
+    dim3 grid((unsigned) ((num_atoms + kThreads - 1) / kThreads), (unsigned) num_anchors, 1);
+    cudaStream_t s = (cudaStream_t) stream;
+    if (precision == DOUBLE) tether_force_kernel<DOUBLE><<<grid, kThreads, 0, s>>>(num_atoms, padded, (const double4*) d_posq, (const double4*) d_x0, k, d_force);
+    else tether_force_kernel<SINGLE><<<grid, kThreads, 0, s>>>(num_atoms, padded, (const float4*) d_posq, (const float4*) d_x0, k, d_force);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t padded, const void* d_posq,
+                                   const void* d_posq_correction, int32_t num_bonds, const int32_t* d_bond_atoms,
+                                   const double* d_bond_params, long long* d_force, void* stream) {
+    (void) d_posq_correction; (void) num_atoms;
+    if (!d_posq || !d_force || (num_bonds > 0 && (!d_bond_atoms || !d_bond_params))) return fail(SEEKR2_B200_ERR_INVALID, "null buffer");
+    cudaStream_t s = (cudaStream_t) stream;
+    CUDA_TRY(cudaMemsetAsync(d_force, 0, sizeof(long long) * 3 * (size_t) padded, s));
+    if (num_bonds > 0) {
+        const int grid = (num_bonds + 127) / 128;
+        if (precision == DOUBLE) bond_force_kernel<DOUBLE><<<grid, 128, 0, s>>>(padded, (const double4*) d_posq, num_bonds, d_bond_atoms, d_bond_params, d_force);
+        else bond_force_kernel<SINGLE><<<grid, 128, 0, s>>>(padded, (const float4*) d_posq, num_bonds, d_bond_atoms, d_bond_params, d_force);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_harness_fill_gaussian(void* d_random, int64_t num_float4, uint64_t seed, uint64_t offset, void* stream) {
+    if (!d_random || num_float4 < 0) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    if (num_float4 == 0) return SEEKR2_B200_OK;
+    const long long grid = (num_float4 + kThreads - 1) / kThreads;
+    fill_gaussian_kernel<<<(unsigned) grid, kThreads, 0, (cudaStream_t) stream>>>((float4*) d_random, num_float4, seed, offset);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+}  // extern "C"
