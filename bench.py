@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SEEKR2 MMVT integrator step on B200.
+
+A "step" is one MMVT integrator step (`kernel.execute`: Langevin update + milestone CV + crossing test
++ predicated bounce + crossing-record append) over one batch of A anchors x N atoms, i.e. ONE launch
+of `fused_step_kernel`.  Workload (BASELINE.json configs[3], the configuration the metric is quoted
+on): trypsin-benzamidine-like system, N = 23 036 atoms, mixed precision, dt = 4 fs, two centroid-pair
+spherical milestones on the 11-atom / 9-atom groups of the reference's demo3, A anchors (Voronoi
+shells) batched per GPU so the working set exceeds L2.  The force buffer is the step's input (what
+OpenMM's force pass hands the integrator): resident in HBM for `value`, copied from pinned host memory
+every step for `e2e`.  Gaussian numbers are generated inside the step kernel (Philox4x32-10).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (see the module docstring of the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT_PS = 0.004           # demo3:59
+N_ATOMS = 23036         # tryp_ben.inpcrd:2
+LIG = [3221, 3222, 3223, 3224, 3225, 3226, 3227, 3228, 3229]                      # demo3:18
+REC = [2478, 2489, 2499, 2535, 2718, 2745, 2769, 2787, 2794, 2867, 2926]          # demo3:20
+STEPS_PER_GRAPH = 32
+BYTES_PER_ATOM_STEP = 152   # mixed precision, in-kernel RNG: R velm 32 + force 24 + posq 16 + corr 16, W 64 (168 with a Gaussian pool)
+
+
+def ns_per_day(steps_per_s: float) -> float:
+    return steps_per_s * DT_PS * 1e-3 * 86400.0
+
+
+def build_workload(num_anchors: int, n_atoms: int, seed: int):
+    import helpers as H
+    from helpers import s2
+    rec = [i for i in REC if i < n_atoms] or list(range(0, 11))
+    lig = [i for i in LIG if i < n_atoms] or list(range(11, 20))
+    syn = H.pair_sphere_system(n_atoms, rec, lig, 1.1, 1.3, seed, dt=DT_PS, tether_k=0.0)
+    # anchors = concentric shells 0.2 nm wide from 0.9 nm
+    shells = [(0.9 + 0.2 * (a % 8), 1.1 + 0.2 * (a % 8)) for a in range(num_anchors)]
+    for a, (rin, rout) in enumerate(shells):
+        syn.boundary_force.setAnchorBondParameters(a, 0, [1.0, -1.0, rin])
+        syn.boundary_force.setAnchorBondParameters(a, 1, [2.0, 1.0, rout])
+    positions = np.empty((num_anchors, n_atoms, 3))
+    base = syn.positions.copy()
+    for a, (rin, rout) in enumerate(shells):
+        syn.positions = base.copy()
+        H.place_pair_distance(syn, rec, lig, 0.5 * (rin + rout))
+        positions[a] = syn.positions
+    syn.positions = base
+    forces = H.gaussian_pool(seed + 99, n_atoms)[:, :3].astype(np.float64)     # static, sigma = 1 kJ/mol/nm
+    return syn, positions, forces, shells
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(num_anchors_per_thread: int, steps: int, warmup: int, n_atoms: int, seed: int) -> dict:
+    """The reference's CPU path (oracle port of the Reference platform, double precision,
+    VARIANT_REFERENCE incl. its three per-step copies) on all host cores, one anchor per thread."""
+    import helpers as H
+    from helpers import L, s2
+    cores = len(os.sched_getaffinity(0))
+    syn, positions, forces, _ = build_workload(cores, n_atoms, seed)
+    integ = H.make_mmvt_integrator(syn, "", "reference")
+    runs = []
+    chunk = 16
+    for a in range(cores):
+        o = H.oracle_for(integ, syn.system, L.DOUBLE, anchor=a, num_anchors=cores)
+        hb = H.make_host_buffers(L.DOUBLE, positions[a], syn.velocities, syn.masses, forces)
+        pool = H.gaussian_pool(seed + a, chunk * hb.posq.shape[0])     # reused cyclically every `chunk` steps
+        runs.append((o, hb, pool))
+    steps = max(chunk, steps // chunk * chunk)
+
+    def work(idx, n):
+        o, hb, pool = runs[idx]
+        for _ in range(n // chunk):
+            o.run(chunk, hb.posq, hb.corr, hb.velm, hb.force, pool, 0, None, 0.0)
+
+    def parallel(n):
+        ts = [threading.Thread(target=work, args=(i, n)) for i in range(cores)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    parallel(chunk * max(1, warmup // chunk))
+    t0 = time.perf_counter()
+    parallel(steps)
+    dt = time.perf_counter() - t0
+    value = ns_per_day(steps / dt) * cores
+    return {"value": value, "unit": "anchor-ns/day", "cores": cores, "kind": "port",
+            "sample": f"{cores} anchors x {n_atoms} atoms x {steps} steps, one anchor per thread, double precision, oracle restatement of ReferenceSeekr2Kernels.cpp:195-339",
+            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--anchors", type=int, default=64, help="anchors batched per GPU")
+    ap.add_argument("--atoms", type=int, default=N_ATOMS)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    seed = 0x5EEC2000 + 4
+    W = max(3, args.warmup)
+    W = (W + STEPS_PER_GRAPH - 1) // STEPS_PER_GRAPH * STEPS_PER_GRAPH   # whole graphs, so the step graph is warm
+    config = {"workload": f"C4 trypsin-benzamidine-like MMVT: {args.atoms} atoms, {args.anchors} anchors (0.2 nm shells) batched per GPU, "
+                          "11+9-atom centroid-pair spherical milestones, dt 4 fs, 300 K, 1/ps, CudaPrecision=mixed",
+              "atoms": args.atoms, "anchors_per_gpu": args.anchors, "dt_fs": DT_PS * 1e3,
+              "l2": "inputs larger than L2 (state+force+random pool > 126 MB)",
+              "force": "static synthetic force buffer (the step's input)", "rng": "in-kernel Philox4x32-10 + Box-Muller (no Gaussian pool)",
+              "steps_per_graph": STEPS_PER_GRAPH}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_steps = args.cpu_steps or max(16, min(args.steps * 4, 16000))
+        res = cpu_reference(1, cpu_steps, 16, args.atoms, seed)
+        cpu_steps = int(round(res['ms_per_step'] and res['seconds'] / (res['ms_per_step'] * 1e-3)))
+        line = {"impl": "reference", "metric": "mmvt_aggregate_anchor_ns_per_day", "value": res["value"], "unit": "anchor-ns/day",
+                "n_gpus": args.gpus, "steps": cpu_steps, "warmup": 16, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": res,
+                "e2e": {"value": res["value"], "unit": "anchor-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import helpers as H
+    from helpers import L, s2
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    A = args.anchors
+
+    def make_context(kind: str):
+        syn, positions, forces, shells = build_workload(A, args.atoms, seed + 1000 * rank)
+        if kind == "mmvt":
+            integ = H.make_mmvt_integrator(syn, "")
+        else:
+            integ = s2.LangevinIntegrator(300.0, 1.0, DT_PS)
+        integ.setRandomNumberSeed(seed + rank)
+        integ.ringCapacity = 1 << 14
+        integ.setUseGraph(True, STEPS_PER_GRAPH)
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=A,
+                         randomPoolSteps=STEPS_PER_GRAPH)
+        ctx.setPositions(positions)
+        ctx.setVelocities(syn.velocities)
+        f = np.zeros((3, ctx.padded_num_atoms), dtype=np.int64)
+        f[:, : args.atoms] = np.rint(forces.T * 4294967296.0).astype(np.int64)
+        ctx.force.copy_(torch.from_numpy(f).to(dev)[None].expand(A, -1, -1))
+        torch.cuda.synchronize()
+        return ctx, integ, f
+
+    def timed_run(ctx, integ, steps, warmup, sampler=None):
+        """Returns (ms total, ms spent inside step-graph replays, launches)."""
+        stream = ctx.stream
+        integ.step(warmup)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pairs = []
+        done = 0
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            integ._update_params()
+            while done < steps:
+                n = min(STEPS_PER_GRAPH, steps - done)
+                ri = integ._prepare_random(n)                      # Philox refill when the pool is exhausted
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                if n == STEPS_PER_GRAPH:
+                    key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, integ._prev)
+                    if integ._graph_key != key:
+                        raise RuntimeError("graph must be warm before the timed region")
+                    L.check(L.lib.seekr2_b200_graph_launch(integ._handle, ctx.stream_ptr))
+                else:
+                    bufs = ctx.buffers()
+                    for s in range(n):
+                        L.check(L.lib.seekr2_b200_step(integ._handle, C.byref(bufs), ri + s * ctx.padded_num_atoms, ctx.stream_ptr))
+                b.record(stream)
+                pairs.append((a, b, n))
+                ctx.random_cursor += n
+                done += n
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        total = ev0.elapsed_time(ev1)
+        kernel_ms = sum(a.elapsed_time(b) for a, b, _ in pairs)
+        return total, kernel_ms, sum(n for _, _, n in pairs), clocks
+
+    # ---- device-resident throughput (value) ---------------------------------------------------------
+    ctx, integ, fhost = make_context("mmvt")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, kernel_ms, launches, clocks = timed_run(ctx, integ, args.steps, W, sampler)
+    fills = 0   # no pool-fill launches: the step kernel generates its Gaussian numbers
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    integ.drain()
+    bounces = sum(integ.getAnchorState(a).num_bounce_steps for a in range(A))
+    records = len(integ.getRecords())
+
+    # end-of-run gather of per-anchor statistics (the only collective of the method; not timed)
+    from seekr2_openmm_plugin_b200 import multi
+    gathered = multi.gather_statistics(integ, world)
+
+    steps_per_s = args.steps / (total_ms * 1e-3)
+    value = ns_per_day(steps_per_s) * A * world
+    atoms_per_launch = A * args.atoms
+    per_launch_s = kernel_ms * 1e-3 / launches
+    achieved = atoms_per_launch * BYTES_PER_ATOM_STEP / per_launch_s / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fused_step_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
+                "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback"}
+
+    # ---- plain Langevin comparator (north star: fused MMVT step <= 1.05 x plain Langevin step) -----
+    ctx_l, integ_l, _ = make_context("langevin")
+    l_total, l_kernel, l_launches, _ = timed_run(ctx_l, integ_l, args.steps, W)
+    mmvt_over_langevin = (kernel_ms / launches) / (l_kernel / l_launches)
+    del ctx_l, integ_l
+
+    # ---- latency mode: ONE anchor per GPU (the literal "8 anchors one per GPU" configuration) ------
+    A_saved, A = A, 1
+    ctx1, integ1, _ = make_context("mmvt")
+    t1, k1, n1, _ = timed_run(ctx1, integ1, args.steps, W)
+    single_anchor = {"ns_per_day_per_anchor": ns_per_day(args.steps / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / args.steps,
+                     "note": "1 anchor per GPU, L2-resident, launch-latency bound; CUDA graph of 32 steps"}
+    del ctx1, integ1
+    A = A_saved
+
+    # ---- end to end through the public API with HOST force buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = torch.from_numpy(np.broadcast_to(fhost[None], (A,) + fhost.shape).copy()).pin_memory()
+        integ.setUseGraph(False)
+        h2d = pinned.numel() * 8
+        d2h = A * C.sizeof(L.AnchorState)
+        e_steps = max(8, min(args.steps, 64))
+
+        def e2e_step():
+            with torch.cuda.stream(ctx.stream):
+                ctx.force.copy_(pinned, non_blocking=True)        # the step's input: forces from the host
+            integ.step(1)                                           # launch + drain (D2H of anchor states + records)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e_dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_dt = float(t.item())
+        e2e = {"value": ns_per_day(e_steps / e_dt) * A * world, "unit": "anchor-ns/day", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": e_dt / e_steps * 1e3,
+               "note": "integrator.step(1) per step: H2D of the force buffer from pinned host memory, one fused launch, D2H of per-anchor state + crossing records; PCIe-bound"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(1, args.cpu_steps or 16000, 16, args.atoms, seed)   # ~10 s at ~0.6 ms per anchor-step
+
+    if rank == 0:
+        line = {"metric": "mmvt_aggregate_anchor_ns_per_day", "value": value, "unit": "anchor-ns/day", "n_gpus": world,
+                "steps": args.steps, "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "ns_per_day_per_anchor": value / (A * world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches + fills, "roofline": roofline, "cpu_baseline": cpu,
+                "mmvt_over_plain_langevin": mmvt_over_langevin, "single_anchor_per_gpu": single_anchor,
+                "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
+                "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

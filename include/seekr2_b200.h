@@ -151,7 +151,7 @@ typedef struct seekr2_b200_buffers {
     void* d_velm;
     const long long* d_force;
     void* d_pos_delta;            /* two-pass path only; may be NULL for the fused step            */
-    const void* d_random;         /* float4 pool                                                   */
+    const void* d_random;         /* float4 pool; NULL = in-kernel Philox (seekr2_b200_set_rng)    */
     int64_t random_anchor_stride; /* float4 elements between consecutive anchors' pools            */
     void* d_old_velm;             /* VARIANT_REFERENCE two-pass path only: mixed4[A][Np] scratch   */
 } seekr2_b200_buffers;
@@ -215,6 +215,12 @@ int seekr2_b200_abi_version(void);
    noisescale = sqrt(BOLTZ*T*(1-vscale^2)).  Cheap; call whenever T, gamma or dt change.          */
 int seekr2_b200_set_params(seekr2_b200_handle h, double temperature, double friction, double step_size);
 int seekr2_b200_get_params(seekr2_b200_handle h, double out_vscale_fscale_noisescale[3]);
+
+/* replaces integration.initRandomNumberGenerator(seed) (CudaSeekr2Kernels.cpp:109,396) for callers
+   that pass d_random == NULL: the step kernels then generate their Gaussian numbers themselves
+   (Philox4x32-10 keyed by `seed`, counter = (atom, anchor_base + anchor, step)) instead of reading
+   OpenMM's pool.  anchor_base makes the streams of different ranks distinct.                        */
+int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base);
 
 /* ---- state the kernels need besides OpenMM's buffers ---------------------------------------- */
 
@@ -298,9 +304,11 @@ int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t
                                    int32_t num_bonds, const int32_t* d_bond_atoms /* [nb][2] */,
                                    const double* d_bond_params /* [nb][2] = r0,k */,
                                    long long* d_force, void* stream);
-/* Philox4x32-10 + Box-Muller Gaussian pool fill (float4, .w = 0)                                   */
-int seekr2_b200_harness_fill_gaussian(void* d_random, int64_t num_float4, uint64_t seed,
-                                      uint64_t offset, void* stream);
+/* fill a Gaussian pool with exactly the numbers the in-kernel generator would use:
+   pool[a*anchor_stride + s*padded + i] = N(seed; atom i, anchor anchor_base + a, step step0 + s)   */
+int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t padded_num_atoms,
+                                  int64_t anchor_stride, int32_t num_steps, uint64_t seed,
+                                  uint32_t anchor_base, uint64_t step0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -127,7 +127,7 @@ class Context:
         x = self._broadcast(positions)
         self.stream.synchronize()
         hi = x.astype(np.float64 if self.precision == L.DOUBLE else np.float32)
-        self.posq[:, : self.num_atoms, :3] = torch.as_tensor(hi, device=self.device)
+        self.posq[:, : self.num_atoms, :3] = torch.as_tensor(np.array(hi, copy=True), device=self.device)
         if self.posq_correction is not None:
             lo = (x - hi.astype(np.float64)).astype(np.float32)
             self.posq_correction[:, : self.num_atoms, :3] = torch.as_tensor(lo, device=self.device)
@@ -137,7 +137,7 @@ class Context:
     def setVelocities(self, velocities) -> None:
         v = self._broadcast(velocities)
         self.stream.synchronize()
-        self.velm[:, : self.num_atoms, :3] = torch.as_tensor(v, dtype=self.mixed_dtype, device=self.device)
+        self.velm[:, : self.num_atoms, :3] = torch.as_tensor(np.array(v, copy=True), dtype=self.mixed_dtype, device=self.device)
         torch.cuda.synchronize(self.device)
         self.groups_dirty = True
 
@@ -190,23 +190,28 @@ class Context:
         if pool.ndim == 2:
             pool = np.broadcast_to(pool[None], (self.num_anchors,) + pool.shape)
         self.stream.synchronize()
-        self.random = torch.as_tensor(np.ascontiguousarray(pool), device=self.device)
+        self.random = torch.as_tensor(np.array(pool, dtype=np.float32, order="C", copy=True), device=self.device)
         self.random_injected = True
         self.random_cursor = 0
         self.random_pool_steps = self.random.shape[1] // self.padded_num_atoms
+
+    def prepareForces(self) -> None:
+        """One-time set-up of the force providers (never inside a graph capture)."""
+        if self._tether and self._x0 is None:
+            f = self._tether[0]
+            self.stream.synchronize()
+            if f.reference_positions is not None:
+                x0 = np.array(self._broadcast(f.reference_positions), copy=True)
+                self._x0 = torch.zeros_like(self.posq)
+                self._x0[:, : self.num_atoms, :3] = torch.as_tensor(x0, dtype=self.real_dtype, device=self.device)
+            else:
+                self._x0 = self.posq.clone()
+            torch.cuda.synchronize(self.device)
 
     def computeForces(self) -> None:
         """Stand-in for ``context.calcForcesAndEnergy(true,false)`` (MmvtLangevinIntegrator.cpp:99)."""
         s = self.stream_ptr
         for f in self._tether:
-            if self._x0 is None:
-                if f.reference_positions is not None:
-                    x0 = self._broadcast(f.reference_positions)
-                    self._x0 = torch.zeros_like(self.posq)
-                    self._x0[:, : self.num_atoms, :3] = torch.as_tensor(x0, dtype=self.real_dtype, device=self.device)
-                else:
-                    self._x0 = self.posq.clone()
-                torch.cuda.synchronize(self.device)
             L.check(L.lib.seekr2_b200_harness_tether_force(
                 self.precision, self.num_anchors, self.num_atoms, self.padded_num_atoms, self.posq.data_ptr(),
                 self.posq_correction.data_ptr() if self.posq_correction is not None else None,

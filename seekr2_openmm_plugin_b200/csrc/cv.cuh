@@ -26,7 +26,7 @@ constexpr unsigned kFullWarp = 0xffffffffu;
 struct EngineDev {
     int num_atoms, padded_num_atoms, num_anchors;
     int num_slots, num_groups, num_boundaries, num_milestone_groups;
-    int variant, flags;
+    int variant, flags_bits;
     int num_src, num_dest, end_on_src;
     int src_groups[SEEKR2_B200_MAX_ELBER];
     int dest_groups[SEEKR2_B200_MAX_ELBER];
@@ -39,6 +39,10 @@ struct EngineDev {
     Record* ring;                // [A][ring_capacity]
     void* slab;                  // [2][A][num_slots] SlabEntry<P>
     int* decision;               // [A] bounce flag of the two-pass path
+    long long* step_shadow;      // [2][A] step index of the launch with that parity (stable during the launch)
+    unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
+    unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
+    int* flags;                  // [2][A] decision hand-off of the fused kernel (0 = not yet, 1 = advance, 3 = bounce)
 };
 
 // shared-memory scratch of the CV phase
@@ -117,14 +121,18 @@ __device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b)
 }
 
 // warp 0: lane b evaluates boundary b of this anchor into shared memory
-__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, int anchor) {
+__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, const Boundary& b) {
     const int lane = threadIdx.x;
     if (lane < e.num_boundaries) {
-        const Boundary b = e.boundaries[(size_t) anchor * e.num_boundaries + lane];
         sh.term[lane] = cv_term(sh, b);
         sh.force_group[lane] = b.force_group;
     }
     __syncwarp();
+}
+__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, int anchor) {
+    Boundary b = {};
+    if (threadIdx.x < e.num_boundaries) b = e.boundaries[(size_t) anchor * e.num_boundaries + threadIdx.x];
+    cv_terms(sh, e, b);
 }
 
 // energy of one force group == context.calcForcesAndEnergy(false, true, 1 << group); one lane

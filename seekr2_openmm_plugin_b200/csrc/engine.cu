@@ -76,6 +76,8 @@ struct seekr2_b200_engine {
     Record* d_ring = nullptr;
     void* d_slab = nullptr;
     int* d_decision = nullptr;
+    int* d_flags = nullptr;
+    long long* d_step_shadow = nullptr;
     // host mirrors for drain
     AnchorState* h_state = nullptr;           // pinned [A]
     std::vector<long long> ring_tail;         // records already drained, per anchor
@@ -123,7 +125,7 @@ int check_bufs(const seekr2_b200_engine* h, const seekr2_b200_buffers* b, bool n
     if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
     if (!b || !b->d_posq || !b->d_velm || !b->d_force) return fail(SEEKR2_B200_ERR_INVALID, "posq, velm and force buffers are required");
     if (h->cfg.precision == MIXED && !b->d_posq_correction) return fail(SEEKR2_B200_ERR_INVALID, "mixed precision needs posqCorrection");
-    if (need_random && !b->d_random) return fail(SEEKR2_B200_ERR_INVALID, "random pool is required");
+    (void) need_random;   // d_random == NULL selects the in-kernel Philox generator
     if (need_delta && !b->d_pos_delta) return fail(SEEKR2_B200_ERR_INVALID, "posDelta is required for the two-pass path");
     if (!h->params_set) return fail(SEEKR2_B200_ERR_INVALID, "seekr2_b200_set_params has not been called");
     return SEEKR2_B200_OK;
@@ -140,7 +142,9 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
 }
 
 template <int P, int KIND> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
-    fused_step_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity);
+    const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
+    fused_step_kernel<P, KIND><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }
@@ -197,7 +201,7 @@ int seekr2_b200_destroy(seekr2_b200_handle h) {
     if (h->graph) cudaGraphDestroy(h->graph);
     cudaFree(h->d_slot_atom); cudaFree(h->d_slot_group); cudaFree(h->d_slot_weight);
     cudaFree(h->d_boundaries); cudaFree(h->d_state); cudaFree(h->d_ring); cudaFree(h->d_slab);
-    cudaFree(h->d_decision);
+    cudaFree(h->d_decision); cudaFree(h->d_flags); cudaFree(h->d_step_shadow);
     if (h->h_state) cudaFreeHost(h->h_state);
     delete h;
     return SEEKR2_B200_OK;
@@ -273,7 +277,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.num_atoms = cfg->num_atoms; d.padded_num_atoms = cfg->padded_num_atoms; d.num_anchors = A;
     d.num_slots = num_slots; d.num_groups = cfg->num_groups; d.num_boundaries = cfg->num_boundaries;
     d.num_milestone_groups = cfg->num_milestone_groups;
-    d.variant = cfg->variant; d.flags = cfg->flags;
+    d.variant = cfg->variant; d.flags_bits = cfg->flags;
     d.num_src = cfg->num_src; d.num_dest = cfg->num_dest; d.end_on_src = cfg->end_on_src_milestone ? 1 : 0;
     for (int i = 0; i < cfg->num_src; i++) d.src_groups[i] = cfg->src_groups[i];
     for (int i = 0; i < cfg->num_dest; i++) d.dest_groups[i] = cfg->dest_groups[i];
@@ -308,6 +312,10 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
     CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * A));
     CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * A));
+    CREATE_TRY(cudaMalloc(&h->d_flags, sizeof(int) * 2 * A));
+    CREATE_TRY(cudaMemset(h->d_flags, 0, sizeof(int) * 2 * A));
+    CREATE_TRY(cudaMalloc(&h->d_step_shadow, sizeof(long long) * 2 * A));
+    CREATE_TRY(cudaMemset(h->d_step_shadow, 0, sizeof(long long) * 2 * A));
     CREATE_TRY(cudaHostAlloc(&h->h_state, sizeof(AnchorState) * A, cudaHostAllocDefault));
     // initialize(): zero statistics, seed counters (CudaSeekr2Kernels.cpp:118-133,151-154,403-404)
     memset(h->h_state, 0, sizeof(AnchorState) * A);
@@ -321,7 +329,8 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
 
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
-    d.decision = h->d_decision;
+    d.decision = h->d_decision; d.flags = h->d_flags; d.step_shadow = h->d_step_shadow;
+    d.rng_seed = 0; d.rng_anchor_base = 0;
     *out = h;
     return SEEKR2_B200_OK;
 #undef CREATE_TRY
@@ -338,6 +347,14 @@ int seekr2_b200_set_params(seekr2_b200_handle h, double temperature, double fric
     h->params[0] = vscale; h->params[1] = fscale; h->params[2] = noisescale;
     h->step_size = step_size;
     h->params_set = true;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "the RNG cannot change inside a graph capture");
+    h->dev.rng_seed = seed;
+    h->dev.rng_anchor_base = anchor_base;
     return SEEKR2_B200_OK;
 }
 
@@ -385,7 +402,7 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
                                 launch_fused_kind<MIXED>(h, bufs, random_index, s),
                                 launch_fused_kind<DOUBLE>(h, bufs, random_index, s));
     if (rc != SEEKR2_B200_OK) return rc;
-    if (h->cfg.kind != SEEKR2_B200_KIND_LANGEVIN) h->parity ^= 1;
+    h->parity ^= 1;   // slab half and decision flag alternate every launch
     if (h->capturing) h->capture_steps++;
     return SEEKR2_B200_OK;
 }
@@ -431,7 +448,7 @@ int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream) {
     h->graph = g;
     h->parity = h->capture_parity0;      // the captured steps have not run yet
     h->graph_steps = h->capture_steps;
-    if (h->cfg.kind != SEEKR2_B200_KIND_LANGEVIN && (h->graph_steps & 1))
+    if (h->graph_steps & 1)
         return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain an even number of fused steps (the slab parity is baked into each launch); got %d", h->graph_steps);
     CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
     return SEEKR2_B200_OK;
@@ -494,6 +511,8 @@ int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int6
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaMemcpy(&h->d_state[anchor].time, &time, sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(&h->d_state[anchor].step_count, &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
+    for (int par = 0; par < 2; par++)
+        CUDA_TRY(cudaMemcpy(&h->d_step_shadow[par * h->cfg.num_anchors + anchor], &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
     return SEEKR2_B200_OK;
 }
 
@@ -584,11 +603,13 @@ int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t
     return SEEKR2_B200_OK;
 }
 
-int seekr2_b200_harness_fill_gaussian(void* d_random, int64_t num_float4, uint64_t seed, uint64_t offset, void* stream) {
-    if (!d_random || num_float4 < 0) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
-    if (num_float4 == 0) return SEEKR2_B200_OK;
-    const long long grid = (num_float4 + kThreads - 1) / kThreads;
-    fill_gaussian_kernel<<<(unsigned) grid, kThreads, 0, (cudaStream_t) stream>>>((float4*) d_random, num_float4, seed, offset);
+int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t padded, int64_t anchor_stride,
+                                  int32_t num_steps, uint64_t seed, uint32_t anchor_base, uint64_t step0, void* stream) {
+    if (!d_random || num_anchors < 1 || padded < 1 || num_steps < 0 || anchor_stride < (int64_t) num_steps * padded)
+        return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    if (num_steps == 0) return SEEKR2_B200_OK;
+    dim3 grid((unsigned) ((padded + kThreads - 1) / kThreads), (unsigned) num_anchors, (unsigned) (num_steps < 32 ? num_steps : 32));
+    fill_pool_kernel<<<grid, kThreads, 0, (cudaStream_t) stream>>>((float4*) d_random, padded, anchor_stride, num_steps, seed, anchor_base, step0);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }

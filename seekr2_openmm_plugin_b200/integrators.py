@@ -48,6 +48,9 @@ class _B200LangevinBase:
         self.useGraph = False
         self.stepsPerGraph = 32
         self.ringCapacity = 0
+        self.useRandomPool = False     # True: Gaussian pool refilled by a harness kernel (OpenMM style)
+        self.rngAnchorBase = 0         # global index of the context's first anchor (multi-GPU runs)
+        self._steps_issued = 0
         self._prev = (None, None, None)
         self._graph_key = None
         self._records: List[L.Record] = []
@@ -133,6 +136,8 @@ class _B200LangevinBase:
             L.lib.seekr2_b200_destroy(self._handle)
             self._handle = C.c_void_p()
         L.check(L.lib.seekr2_b200_create(C.byref(cfg), C.byref(self._handle)))
+        L.check(L.lib.seekr2_b200_set_rng(self._handle, self.randomNumberSeed, self.rngAnchorBase))
+        self._steps_issued = 0
         self._prev = (None, None, None)
         self._graph_key = None
         self._records = []
@@ -177,20 +182,23 @@ class _B200LangevinBase:
 
     def _prepare_random(self, steps_needed: int) -> int:
         """``integration.prepareRandomNumbers(paddedNumAtoms)`` (CudaSeekr2Kernels.cpp:214): returns
-        the pool index of the next step, refilling the pool (Philox) when it is exhausted."""
+        the pool index of the next step.  Three sources of Gaussian numbers:
+          - injected pool (``context.setRandomPool``): parity tests, "identical injected random numbers";
+          - ``useRandomPool``: a device pool refilled with the Philox harness kernel when exhausted;
+          - default: no pool at all, the step kernels generate the numbers themselves (same Philox)."""
         ctx = self.context
         Np = ctx.padded_num_atoms
+        if ctx.random is None and not self.useRandomPool:
+            return 0                              # in-kernel generator: the index is unused
         if ctx.random is None:
             ctx.random = torch.empty((ctx.num_anchors, ctx.random_pool_steps * Np, 4), dtype=torch.float32, device=ctx.device)
             ctx.random_cursor = ctx.random_pool_steps
-            self._pool_generation = 0
         if ctx.random_cursor + steps_needed > ctx.random_pool_steps:
             if ctx.random_injected:
                 raise L.Seekr2Error(L.ERR_INVALID, "injected random pool exhausted")
-            n = ctx.random.numel() // 4
-            L.check(L.lib.seekr2_b200_harness_fill_gaussian(ctx.random.data_ptr(), n, self.randomNumberSeed,
-                                                            self._pool_generation * n, ctx.stream_ptr))
-            self._pool_generation += 1
+            L.check(L.lib.seekr2_b200_harness_fill_pool(ctx.random.data_ptr(), ctx.num_anchors, Np, int(ctx.random.shape[1]),
+                                                        ctx.random_pool_steps, self.randomNumberSeed, self.rngAnchorBase,
+                                                        self._steps_issued, ctx.stream_ptr))
             ctx.random_cursor = 0
         return ctx.random_cursor * Np
 
@@ -218,6 +226,7 @@ class _B200LangevinBase:
         self._update_params()
         if self.stepMode == "two_pass":
             ctx.ensure_two_pass_buffers(self.variant == L.VARIANT_REFERENCE and self.KIND == L.KIND_MMVT)
+        ctx.prepareForces()
         self._first_step_check()
         self._before_first_step()
         done = 0
@@ -225,12 +234,13 @@ class _B200LangevinBase:
             S = self.stepsPerGraph
             while steps - done >= S:
                 ri = self._prepare_random(S)
-                key = (ri, ctx.random.data_ptr(), self._prev)
+                key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, self._prev)
                 if self._graph_key != key:
                     self._capture(S, ri)
                     self._graph_key = key
                 L.check(L.lib.seekr2_b200_graph_launch(self._handle, ctx.stream_ptr))
                 ctx.random_cursor += S
+                self._steps_issued += S
                 done += S
         while done < steps:
             ri = self._prepare_random(1)
@@ -238,6 +248,7 @@ class _B200LangevinBase:
                 ctx.computeForces()
             self._execute(ctx.buffers(), ri)
             ctx.random_cursor += 1
+            self._steps_issued += 1
             done += 1
         self._after_steps()
 
@@ -264,22 +275,35 @@ class _B200LangevinBase:
         self.drain()
 
     # -- results -------------------------------------------------------------------------------------
+    _DRAIN_CHUNK = 1 << 14
+
     def drain(self) -> List[L.Record]:
         """Fetch new crossing records and append them to the output file(s)."""
         ctx = self.context
-        cap = max(1, int(self._config.ring_capacity or 4096)) * ctx.num_anchors
-        buf = (L.Record * cap)()
-        n = C.c_int64(0)
-        rc = L.lib.seekr2_b200_drain(self._handle, buf, cap, C.byref(n), ctx.stream_ptr)
-        new = [self._copy_record(buf[i]) for i in range(n.value)]
-        self._records.extend(new)
+        if getattr(self, "_drain_buf", None) is None:
+            self._drain_buf = (L.Record * self._DRAIN_CHUNK)()
+        buf = self._drain_buf
         names = self.outputFileNames()
-        if names and new:
-            for a in range(ctx.num_anchors):
-                labels = self._labels(a)
-                L.check(L.lib.seekr2_b200_append_records(self.KIND, names[a].encode(), buf, n.value, a,
-                                                         _i32_array(labels), len(labels), self._num_src()))
-        L.check(rc)
+        new: List[L.Record] = []
+        status = L.OK
+        while True:
+            n = C.c_int64(0)
+            rc = L.lib.seekr2_b200_drain(self._handle, buf, self._DRAIN_CHUNK, C.byref(n), ctx.stream_ptr)
+            if rc not in (L.OK, L.ERR_RING_OVERFLOW):
+                L.check(rc)
+            status = status or rc
+            got = [self._copy_record(buf[i]) for i in range(n.value)]
+            new.extend(got)
+            if names and got:
+                for a in sorted({r.anchor for r in got}):
+                    labels = self._labels(a)
+                    L.check(L.lib.seekr2_b200_append_records(self.KIND, names[a].encode(), buf, n.value, a,
+                                                             _i32_array(labels), len(labels), self._num_src()))
+            if n.value < self._DRAIN_CHUNK:
+                break
+        self._records.extend(new)
+        if status != L.OK:
+            raise L.Seekr2Error(status, "crossing ring overflowed: records were lost; drain more often or raise ringCapacity")
         return new
 
     @staticmethod
