@@ -22,6 +22,8 @@ constexpr double kFixedScale = 1099511627776.0;           // 2^40
 constexpr double kFixedInvScale = 1.0 / 1099511627776.0;  // 2^-40
 constexpr unsigned kFullWarp = 0xffffffffu;
 
+constexpr int kInlineSlots = 256;   // group slots whose atom index travels in the kernel parameters
+
 // everything a step kernel needs besides the caller's buffers; passed by value
 struct EngineDev {
     int num_atoms, padded_num_atoms, num_anchors;
@@ -42,6 +44,10 @@ struct EngineDev {
     long long* step_shadow;      // [2][A] step index of the launch with that parity (stable during the launch)
     unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
     unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
+    // atom index of the first kInlineSlots group slots, kept in the kernel parameters (constant bank):
+    // the decide block can then issue its force gathers in the same round trip as the slab loads
+    // instead of waiting for slot_atom[] to come back from memory first
+    int slot_atom_inline[kInlineSlots];
     int* flags;                  // [2][A] decision hand-off of the fused kernel (0 = not yet, 1 = advance, 3 = bounce)
 };
 
@@ -52,6 +58,10 @@ struct CvShared {
     int force_group[SEEKR2_B200_MAX_BOUNDARIES];
     int bounce;
 };
+
+__device__ __forceinline__ int slot_atom_of(const EngineDev& e, int s) {
+    return s < kInlineSlots ? e.slot_atom_inline[s] : e.slot_atom[s];
+}
 
 __device__ __forceinline__ void cv_clear(CvShared& sh, int num_groups) {
     if (threadIdx.x < num_groups * 3) sh.acc[threadIdx.x] = 0;

@@ -282,6 +282,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     for (int i = 0; i < cfg->num_src; i++) d.src_groups[i] = cfg->src_groups[i];
     for (int i = 0; i < cfg->num_dest; i++) d.dest_groups[i] = cfg->dest_groups[i];
     d.ring_capacity = h->cfg.ring_capacity;
+    for (int i = 0; i < kInlineSlots; i++) d.slot_atom_inline[i] = i < num_slots ? slot_atom[i] : 0;
 
     auto bail = [&](int code) { seekr2_b200_destroy(h); return code; };
 #define CREATE_TRY(call)                                                                            \
