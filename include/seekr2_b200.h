@@ -291,6 +291,12 @@ int seekr2_b200_append_records(int32_t kind, const char* path, const seekr2_b200
 int seekr2_b200_write_statistics(const char* path, const seekr2_b200_anchor_state* st,
                                  const int32_t* labels, int32_t num_labels);
 
+/* debug: when d_probe (int64[8*A + 4], device) is set the fused kernel records %globaltimer stamps of
+   each decide block ([0] start, [1] loads returned, [2] atoms advanced, [3] accumulated, [4] groups
+   reduced, [5] decision published, [6] earliest streaming arrival of the anchor) and the streaming
+   blocks' total wait ([8A..]: blocks that waited, polls, ns).  NULL disables it.                     */
+int seekr2_b200_debug_set_probe(seekr2_b200_handle h, void* d_probe);
+
 /* ---- harness kernels (stand-ins for what OpenMM supplies; not part of the drop-in path) -------- */
 
 /* harmonic tether force  F = -k (x - x0)  written as int64 fixed point (value * 2^32)              */

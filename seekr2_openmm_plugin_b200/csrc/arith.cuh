@@ -67,6 +67,50 @@ __device__ __forceinline__ long long ld_ro(const long long* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+// ---- L2-pinned accesses of the decide blocks ------------------------------------------------------
+// The few KB a decide block needs every step (slot metadata, slab entries, the group atoms' force
+// words) are tagged evict_last so the ~250 MB that stream through L2 per launch do not push them
+// out: the latency-critical gathers then hit L2 instead of queueing at HBM.
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int ld_keep_i32(const int* p, unsigned long long pol) {
+    int r;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p, unsigned long long pol) {
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ long long ld_keep_s64(const long long* p, unsigned long long pol) {
+    long long r;
+    asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double4 ld_keep(const double4* p, unsigned long long pol) {
+    double4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_keep(float4* p, const float4& v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(double4* p, const double4& v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

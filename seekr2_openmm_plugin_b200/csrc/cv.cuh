@@ -22,8 +22,6 @@ constexpr double kFixedScale = 1099511627776.0;           // 2^40
 constexpr double kFixedInvScale = 1.0 / 1099511627776.0;  // 2^-40
 constexpr unsigned kFullWarp = 0xffffffffu;
 
-constexpr int kInlineSlots = 256;   // group slots whose atom index travels in the kernel parameters
-
 // everything a step kernel needs besides the caller's buffers; passed by value
 struct EngineDev {
     int num_atoms, padded_num_atoms, num_anchors;
@@ -44,10 +42,10 @@ struct EngineDev {
     long long* step_shadow;      // [2][A] step index of the launch with that parity (stable during the launch)
     unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
     unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
-    // atom index of the first kInlineSlots group slots, kept in the kernel parameters (constant bank):
-    // the decide block can then issue its force gathers in the same round trip as the slab loads
-    // instead of waiting for slot_atom[] to come back from memory first
-    int slot_atom_inline[kInlineSlots];
+    long long* probe;            // optional timing probe (debug, seekr2_b200_debug_set_probe)
+    int* head_start;             // [2] decide blocks that have issued their gathers (per launch parity)
+    int first_wave_blocks;       // streaming blocks resident at kernel start (they wait for head_start)
+    int head_start_target;       // A x warps per decide block that hold group slots
     int* flags;                  // [2][A] decision hand-off of the fused kernel (0 = not yet, 1 = advance, 3 = bounce)
 };
 
@@ -59,12 +57,19 @@ struct CvShared {
     int bounce;
 };
 
-__device__ __forceinline__ int slot_atom_of(const EngineDev& e, int s) {
-    return s < kInlineSlots ? e.slot_atom_inline[s] : e.slot_atom[s];
-}
-
 __device__ __forceinline__ void cv_clear(CvShared& sh, int num_groups) {
     if (threadIdx.x < num_groups * 3) sh.acc[threadIdx.x] = 0;
+}
+
+// sum over the 32 lanes of a converged warp, modulo 2^64 (exact whenever the true sum fits in int64)
+__device__ __forceinline__ long long warp_sum_s64(long long q) {
+    const unsigned long long u = (unsigned long long) q;
+    const unsigned s0 = __reduce_add_sync(kFullWarp, (unsigned) (u & 0xFFFFu));
+    const unsigned s1 = __reduce_add_sync(kFullWarp, (unsigned) ((u >> 16) & 0xFFFFu));
+    const unsigned s2 = __reduce_add_sync(kFullWarp, (unsigned) ((u >> 32) & 0xFFFFu));
+    const int s3 = __reduce_add_sync(kFullWarp, (int) (q >> 48));                    // signed top limb
+    return (long long) (((unsigned long long) (long long) s3 << 48) + ((unsigned long long) s2 << 32) +
+                        ((unsigned long long) s1 << 16) + (unsigned long long) s0);
 }
 
 // Adds one slot's weighted position to its group's fixed-point accumulator.  Must be called by all
@@ -84,12 +89,9 @@ __device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, d
     const int gref = __shfl_sync(kFullWarp, g, __ffs(vmask) - 1);
     const bool uniform = __all_sync(kFullWarp, !valid || g == gref);
     if (uniform) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            qx += __shfl_xor_sync(kFullWarp, qx, off);
-            qy += __shfl_xor_sync(kFullWarp, qy, off);
-            qz += __shfl_xor_sync(kFullWarp, qz, off);
-        }
+        // exact 64-bit warp sums from four 16-bit limbs each: every limb sum fits in 21 bits, so the
+        // twelve REDUX.SUM are independent single instructions (no 5-level shuffle chain)
+        qx = warp_sum_s64(qx); qy = warp_sum_s64(qy); qz = warp_sum_s64(qz);
         if ((threadIdx.x & 31) == 0) {
             atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 0], (unsigned long long) qx);
             atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 1], (unsigned long long) qy);

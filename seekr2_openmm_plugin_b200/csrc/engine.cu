@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -223,9 +224,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     if (cfg->num_groups > 0 && (!cfg->group_offsets || !cfg->group_atoms || !cfg->group_weights)) return fail(SEEKR2_B200_ERR_INVALID, "group arrays missing");
     if (cfg->num_boundaries > 0 && !cfg->boundaries) return fail(SEEKR2_B200_ERR_INVALID, "boundary array missing");
 
-    const int num_slots = cfg->num_groups > 0 ? cfg->group_offsets[cfg->num_groups] : 0;
-    std::vector<int> slot_atom(num_slots), slot_group(num_slots);
-    std::vector<double> slot_weight(num_slots);
+    // Group slots, padded so that every warp of a decide block holds slots of ONE group only: each
+    // group's slot range is rounded up to a multiple of 32 with weight-0 copies of its last atom.
+    // The warp-level reduction of the centroid sums then never mixes groups (no per-lane atomics).
+    std::vector<int> slot_atom, slot_group;
+    std::vector<double> slot_weight;
     for (int g = 0; g < cfg->num_groups; g++) {
         const int lo = cfg->group_offsets[g], hi = cfg->group_offsets[g + 1];
         if (hi <= lo) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d is empty", g);
@@ -235,11 +238,17 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         if (!(sum > 0.0)) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d has non-positive total weight", g);
         for (int j = lo; j < hi; j++) {
             if (cfg->group_atoms[j] < 0 || cfg->group_atoms[j] >= cfg->num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "group %d references atom %d outside [0,%d)", g, cfg->group_atoms[j], cfg->num_atoms);
-            slot_atom[j] = cfg->group_atoms[j];
-            slot_group[j] = g;
-            slot_weight[j] = cfg->group_weights[j] / sum;
+            slot_atom.push_back(cfg->group_atoms[j]);
+            slot_group.push_back(g);
+            slot_weight.push_back(cfg->group_weights[j] / sum);
+        }
+        while (slot_atom.size() % 32 != 0) {
+            slot_atom.push_back(cfg->group_atoms[hi - 1]);
+            slot_group.push_back(g);
+            slot_weight.push_back(0.0);
         }
     }
+    const int num_slots = (int) slot_atom.size();
     for (int a = 0; a < cfg->num_anchors; a++)
         for (int i = 0; i < cfg->num_boundaries; i++) {
             const seekr2_b200_boundary& bd = cfg->boundaries[(size_t) a * cfg->num_boundaries + i];
@@ -282,7 +291,6 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     for (int i = 0; i < cfg->num_src; i++) d.src_groups[i] = cfg->src_groups[i];
     for (int i = 0; i < cfg->num_dest; i++) d.dest_groups[i] = cfg->dest_groups[i];
     d.ring_capacity = h->cfg.ring_capacity;
-    for (int i = 0; i < kInlineSlots; i++) d.slot_atom_inline[i] = i < num_slots ? slot_atom[i] : 0;
 
     auto bail = [&](int code) { seekr2_b200_destroy(h); return code; };
 #define CREATE_TRY(call)                                                                            \
@@ -313,8 +321,8 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
     CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * A));
     CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * A));
-    CREATE_TRY(cudaMalloc(&h->d_flags, sizeof(int) * 2 * A));
-    CREATE_TRY(cudaMemset(h->d_flags, 0, sizeof(int) * 2 * A));
+    CREATE_TRY(cudaMalloc(&h->d_flags, sizeof(int) * (2 * A + 2)));      // [2][A] flags + [2] head-start counters
+    CREATE_TRY(cudaMemset(h->d_flags, 0, sizeof(int) * (2 * A + 2)));
     CREATE_TRY(cudaMalloc(&h->d_step_shadow, sizeof(long long) * 2 * A));
     CREATE_TRY(cudaMemset(h->d_step_shadow, 0, sizeof(long long) * 2 * A));
     CREATE_TRY(cudaHostAlloc(&h->h_state, sizeof(AnchorState) * A, cudaHostAllocDefault));
@@ -331,7 +339,18 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
     d.decision = h->d_decision; d.flags = h->d_flags; d.step_shadow = h->d_step_shadow;
-    d.rng_seed = 0; d.rng_anchor_base = 0;
+    d.rng_seed = 0; d.rng_anchor_base = 0; d.probe = nullptr;
+    d.head_start = h->d_flags + 2 * A;
+    {
+        cudaDeviceProp prop;
+        CREATE_TRY(cudaGetDeviceProperties(&prop, h->device));
+        // streaming blocks resident when the kernel starts: SMs x blocks per SM, minus the decide blocks
+        d.first_wave_blocks = prop.multiProcessorCount * kFusedMinBlocks - A;
+        if (d.first_wave_blocks < 0) d.first_wave_blocks = 0;
+        if (const char* hs = getenv("SEEKR2_B200_HEAD_START")) if (hs[0] == '0') d.first_wave_blocks = 0;   // tuning knob
+        const int slot_warps = ((num_slots < kThreads ? num_slots : kThreads) + 31) / 32;
+        d.head_start_target = A * slot_warps;
+    }
     *out = h;
     return SEEKR2_B200_OK;
 #undef CREATE_TRY
@@ -356,6 +375,12 @@ int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_bas
     if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "the RNG cannot change inside a graph capture");
     h->dev.rng_seed = seed;
     h->dev.rng_anchor_base = anchor_base;
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_debug_set_probe(seekr2_b200_handle h, void* d_probe) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    h->dev.probe = (long long*) d_probe;
     return SEEKR2_B200_OK;
 }
 
