@@ -1,0 +1,163 @@
+/* OpenMM KernelImpls over the B200 C ABI: the replacement of
+ * seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.cpp:63-599.  NOT COMPILED here (no OpenMM).
+ *
+ * Per step the reference does Part1 -> applyConstraints -> Part2 -> computeVirtualSites ->
+ * calcForcesAndEnergy(false,true,mask) [blocking readback] -> host crossing block -> mmvtBounce.
+ * Here: seekr2_b200_kick -> applyConstraints -> seekr2_b200_finish (decision + bounce on the device);
+ * the crossing records are drained when the ring is polled (every step by default, to keep OpenMM's
+ * Context time in step for Elber's setTime(0); `drainInterval` steps otherwise).  The first-step test
+ * (:205-210) and the Elber force-group check (:415-436) keep their exceptions and messages. */
+#include "B200Seekr2Kernels.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/internal/ContextImpl.h"
+#include "openmm/cuda/CudaIntegrationUtilities.h"
+#include <fstream>
+
+using namespace OpenMM;
+namespace Seekr2Plugin {
+
+B200StepKernelBase::~B200StepKernelBase() {
+    cu.setAsCurrent();                                            /* :74-80 */
+    seekr2_b200_destroy(handle);
+}
+
+void B200StepKernelBase::check(int status) const {
+    if (status != SEEKR2_B200_OK) throw OpenMMException(seekr2_b200_last_error());
+}
+
+void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, int seed) {
+    cu.getPlatformData().initializeContexts(system);               /* :106 */
+    cu.setAsCurrent();
+    cu.getIntegrationUtilities().initRandomNumberGenerator(seed);  /* :109 -- OpenMM's pool is used */
+    boundarySet = recogniseBoundaries(system);
+    cfg.abi_version = SEEKR2_B200_ABI_VERSION;
+    cfg.precision = cu.getUseDoublePrecision() ? SEEKR2_B200_DOUBLE : cu.getUseMixedPrecision() ? SEEKR2_B200_MIXED : SEEKR2_B200_SINGLE;
+    cfg.variant = SEEKR2_B200_VARIANT_CUDA;
+    cfg.device = cu.getDeviceIndex();
+    cfg.num_anchors = 1;
+    cfg.num_atoms = cu.getNumAtoms();
+    cfg.padded_num_atoms = cu.getPaddedNumAtoms();
+    cfg.num_groups = (int) boundarySet.groupOffsets.size() - 1;
+    cfg.group_offsets = boundarySet.groupOffsets.data();
+    cfg.group_atoms = boundarySet.groupAtoms.data();
+    cfg.group_weights = boundarySet.groupWeights.data();
+    cfg.num_boundaries = (int) boundarySet.boundaries.size();
+    cfg.boundaries = boundarySet.boundaries.data();
+    check(seekr2_b200_create(&cfg, &handle));
+}
+
+seekr2_b200_buffers B200StepKernelBase::buffers() {
+    CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
+    seekr2_b200_buffers b{};
+    b.d_posq = (void*) cu.getPosq().getDevicePointer();
+    b.d_posq_correction = cu.getUseMixedPrecision() ? (void*) cu.getPosqCorrection().getDevicePointer() : nullptr;   /* :231 */
+    b.d_velm = (void*) cu.getVelm().getDevicePointer();
+    b.d_force = (const long long*) cu.getForce().getDevicePointer();
+    b.d_pos_delta = (void*) integration.getPosDelta().getDevicePointer();
+    b.d_random = (const void*) integration.getRandom().getDevicePointer();
+    b.random_anchor_stride = 0;
+    return b;
+}
+
+void B200StepKernelBase::stepTwoPass(double temperature, double friction, double stepSize, double tolerance) {
+    CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
+    integration.setNextStepSize(stepSize);                         /* :187 */
+    if (temperature != prevTemp || friction != prevFriction || stepSize != prevStepSize) {   /* :188-203 */
+        check(seekr2_b200_set_params(handle, temperature, friction, stepSize));
+        prevTemp = temperature; prevFriction = friction; prevStepSize = stepSize;
+    }
+    seekr2_b200_buffers b = buffers();
+    void* stream = (void*) cu.getCurrentStream();
+    const int randomIndex = integration.prepareRandomNumbers(cu.getPaddedNumAtoms());       /* :214 */
+    check(seekr2_b200_kick(handle, &b, (uint32_t) randomIndex, stream));                    /* Part1 :215-223 */
+    integration.applyConstraints(tolerance);                                                /* :227 */
+    check(seekr2_b200_finish(handle, &b, stream));                                          /* Part2 + CV + crossing + bounce :231-358 */
+    integration.computeVirtualSites();                                                      /* :239 (groups with virtual sites are refused) */
+}
+
+void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc) {
+    records.resize(4096);
+    int64_t n = 0;
+    check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
+    if (n > 0) check(seekr2_b200_append_records(kind, file.c_str(), records.data(), n, 0, labels.data(), (int32_t) labels.size(), numSrc));
+    records.resize((size_t) n);
+}
+
+/* ---- MMVT ------------------------------------------------------------------------------------------- */
+
+void B200IntegrateMmvtLangevinStepKernel::initialize(const System& system, const MmvtLangevinIntegrator& integrator) {
+    seekr2_b200_config cfg{};
+    cfg.kind = SEEKR2_B200_KIND_MMVT;
+    cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
+    const int32_t counter0 = integrator.getBounceCounter();        /* :151 */
+    cfg.bounce_counter0 = &counter0;
+    create(system, cfg, integrator.getRandomNumberSeed());
+    outputFileName = integrator.getOutputFileName();
+    saveStatisticsFileName = integrator.getSaveStatisticsFileName();
+    if (!integrator.getSaveStateFileName().empty())
+        throw OpenMMException("B200 SEEKR2 plugin: saveStateFileName is not supported yet (SURVEY.md 8f rank 2)");
+    for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) milestoneGroups.push_back(integrator.getMilestoneGroup(i));
+    check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, outputFileName.c_str()));          /* :158-171 */
+}
+
+void B200IntegrateMmvtLangevinStepKernel::execute(ContextImpl& context, const MmvtLangevinIntegrator& integrator) {
+    cu.setAsCurrent();
+    if (cu.getStepCount() <= 0) {                                  /* :205-210 */
+        seekr2_b200_buffers b = buffers();
+        check(seekr2_b200_check_first_step(handle, &b, nullptr, (void*) cu.getCurrentStream()));
+    }
+    stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    drainTo(outputFileName, SEEKR2_B200_KIND_MMVT, milestoneGroups, 0);
+    if (!saveStatisticsFileName.empty() && !records.empty()) {     /* :313-345 */
+        seekr2_b200_anchor_state st;
+        check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+        check(seekr2_b200_write_statistics(saveStatisticsFileName.c_str(), &st, milestoneGroups.data(), (int32_t) milestoneGroups.size()));
+    }
+    cu.setTime(cu.getTime() + integrator.getStepSize());           /* :362-365 */
+    cu.setStepCount(cu.getStepCount() + 1);
+    cu.reorderAtoms();
+}
+
+double B200IntegrateMmvtLangevinStepKernel::computeKineticEnergy(ContextImpl&, const MmvtLangevinIntegrator& integrator) {
+    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :368-370 */
+}
+
+/* ---- Elber ------------------------------------------------------------------------------------------ */
+
+void B200IntegrateElberLangevinStepKernel::initialize(const System& system, const ElberLangevinIntegrator& integrator) {
+    seekr2_b200_config cfg{};
+    cfg.kind = SEEKR2_B200_KIND_ELBER;
+    std::vector<int32_t> src, dest;
+    for (int i = 0; i < integrator.getNumSrcMilestoneGroups(); i++) src.push_back(integrator.getSrcMilestoneGroup(i));
+    for (int i = 0; i < integrator.getNumDestMilestoneGroups(); i++) dest.push_back(integrator.getDestMilestoneGroup(i));
+    cfg.num_src = (int) src.size(); cfg.src_groups = src.data();
+    cfg.num_dest = (int) dest.size(); cfg.dest_groups = dest.data();
+    cfg.end_on_src_milestone = integrator.getEndOnSrcMilestone();  /* :414 */
+    const int32_t counter0 = integrator.getCrossingCounter();      /* :403 */
+    cfg.crossing_counter0 = &counter0;
+    create(system, cfg, integrator.getRandomNumberSeed());          /* missing force group -> the reference's message (:421-422) */
+    outputFileName = integrator.getOutputFileName();
+    labels = src; labels.insert(labels.end(), dest.begin(), dest.end());
+    numSrc = (int) src.size();
+    check(seekr2_b200_write_header(SEEKR2_B200_KIND_ELBER, outputFileName.c_str()));         /* :447-462 */
+}
+
+void B200IntegrateElberLangevinStepKernel::execute(ContextImpl& context, const ElberLangevinIntegrator& integrator) {
+    cu.setAsCurrent();
+    /* Elber's crossing test looks at the context time (:533,:558) and may reset it (:545): the engine
+       keeps that clock on the device; mirror OpenMM's copy into it before and out of it after */
+    check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), (void*) cu.getCurrentStream()));
+    stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    drainTo(outputFileName, SEEKR2_B200_KIND_ELBER, labels, numSrc);
+    seekr2_b200_anchor_state st;
+    check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+    cu.setTime(st.time);                                           /* already advanced by stepSize (:592) */
+    cu.setStepCount(cu.getStepCount() + 1);
+    cu.reorderAtoms();
+}
+
+double B200IntegrateElberLangevinStepKernel::computeKineticEnergy(ContextImpl&, const ElberLangevinIntegrator& integrator) {
+    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :597-599 */
+}
+
+}  // namespace Seekr2Plugin

@@ -1,0 +1,72 @@
+/* Walks the System's CustomCentroidBondForce objects and emits the typed boundary descriptors of
+ * include/seekr2_b200.h.  Same recognition rules as the Python harness
+ * (seekr2_openmm_plugin_b200/system.py::_recognise), which IS tested.  NOT COMPILED here (no OpenMM). */
+#include "B200Seekr2Kernels.h"
+#include "openmm/CustomCentroidBondForce.h"
+#include "openmm/OpenMMException.h"
+#include <algorithm>
+#include <map>
+#include <regex>
+
+using namespace OpenMM;
+namespace Seekr2Plugin {
+
+namespace {
+struct Typed { int type, style, axis; double kSign; std::string thr; std::string cx, cy, cz; };
+
+Typed recognise(std::string e, int numGroups) {
+    e.erase(std::remove_if(e.begin(), e.end(), ::isspace), e.end());
+    Typed t{0, SEEKR2_B200_STYLE_RAW, 0, 1.0, "radius", "", "", ""};
+    std::smatch m;
+    if (std::regex_match(e, m, std::regex(R"(bitcode\*step\((.*)\))"))) { t.style = SEEKR2_B200_STYLE_STEP; e = m[1]; }
+    if (!e.empty() && e[0] == '-') { t.kSign = -1.0; e = e.substr(1); }
+    if (!std::regex_match(e, m, std::regex(R"(k\*\((.*)\))"))) throw OpenMMException("B200 SEEKR2 plugin: cannot type boundary expression");
+    std::string u = m[1];
+    if (numGroups == 2 && std::regex_match(u, m, std::regex(R"(distance\(g1,g2\)\^2-(\w+)\^2)"))) { t.type = SEEKR2_B200_CV_SPHERE_PAIR; t.thr = m[1]; return t; }
+    if (numGroups == 1 && std::regex_match(u, m, std::regex(R"(\(x1-(\w+)\)\^2\+\(y1-(\w+)\)\^2\+\(z1-(\w+)\)\^2-(\w+)\^2)"))) {
+        t.type = SEEKR2_B200_CV_SPHERE_FIXED; t.cx = m[1]; t.cy = m[2]; t.cz = m[3]; t.thr = m[4]; return t; }
+    if (numGroups == 1 && std::regex_match(u, m, std::regex(R"(([xyz])1-(\w+))"))) {
+        t.type = SEEKR2_B200_CV_PLANE; t.axis = std::string("xyz").find(m[1].str()[0]); t.thr = m[2]; return t; }
+    throw OpenMMException("B200 SEEKR2 plugin: cannot type boundary expression");
+}
+}  // namespace
+
+B200BoundarySet recogniseBoundaries(const System& system) {
+    B200BoundarySet out;
+    for (int f = 0; f < system.getNumForces(); f++) {
+        const auto* force = dynamic_cast<const CustomCentroidBondForce*>(&system.getForce(f));
+        if (force == nullptr) continue;
+        if (force->usesPeriodicBoundaryConditions()) throw OpenMMException("B200 SEEKR2 plugin: periodic centroid boundaries are not supported");
+        const Typed t = recognise(force->getEnergyFunction(), force->getNumGroupsPerBond());
+        const int base = (int) out.groupOffsets.size() - 1;
+        for (int g = 0; g < force->getNumGroups(); g++) {
+            std::vector<int> particles; std::vector<double> weights;
+            force->getGroupParameters(g, particles, weights);
+            for (size_t i = 0; i < particles.size(); i++) {
+                out.groupAtoms.push_back(particles[i]);
+                /* without explicit weights a centroid group is mass weighted */
+                out.groupWeights.push_back(weights.empty() ? system.getParticleMass(particles[i]) : weights[i]);
+            }
+            out.groupOffsets.push_back((int32_t) out.groupAtoms.size());
+        }
+        std::map<std::string, int> index;
+        for (int p = 0; p < force->getNumPerBondParameters(); p++) index[force->getPerBondParameterName(p)] = p;
+        auto value = [&](const std::vector<double>& params, const std::string& name, double fallback) {
+            auto it = index.find(name); return it == index.end() ? fallback : params[it->second]; };
+        for (int b = 0; b < force->getNumBonds(); b++) {
+            std::vector<int> groups; std::vector<double> params;
+            force->getBondParameters(b, groups, params);
+            seekr2_b200_boundary bd{};
+            bd.type = t.type; bd.style = t.style; bd.axis = t.axis; bd.force_group = force->getForceGroup();
+            bd.group_a = base + groups[0];
+            bd.group_b = t.type == SEEKR2_B200_CV_SPHERE_PAIR ? base + groups[1] : 0;
+            bd.bitcode = value(params, "bitcode", 1.0);
+            bd.k = t.kSign * value(params, "k", 1.0);
+            bd.threshold = value(params, t.thr, 0.0);
+            if (t.type == SEEKR2_B200_CV_SPHERE_FIXED) { bd.center[0] = value(params, t.cx, 0); bd.center[1] = value(params, t.cy, 0); bd.center[2] = value(params, t.cz, 0); }
+            out.boundaries.push_back(bd);
+        }
+    }
+    return out;
+}
+}  // namespace Seekr2Plugin
