@@ -147,7 +147,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=2048)
     ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--anchors", type=int, default=64, help="anchors batched per GPU")
+    ap.add_argument("--anchors", type=int, default=128, help="anchors batched per GPU")
     ap.add_argument("--atoms", type=int, default=N_ATOMS)
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -163,14 +163,14 @@ def main() -> None:
     config = {"workload": f"C4 trypsin-benzamidine-like MMVT: {args.atoms} atoms, {args.anchors} anchors (0.2 nm shells) batched per GPU, "
                           "11+9-atom centroid-pair spherical milestones, dt 4 fs, 300 K, 1/ps, CudaPrecision=mixed",
               "atoms": args.atoms, "anchors_per_gpu": args.anchors, "dt_fs": DT_PS * 1e3,
-              "l2": "inputs larger than L2 (state+force+random pool > 126 MB)",
+              "l2": "inputs larger than L2: state 260 MB + force 71 MB per step vs 126 MB L2; no flush needed",
               "force": "static synthetic force buffer (the step's input)", "rng": "in-kernel Philox4x32-10 + Box-Muller (no Gaussian pool)",
               "steps_per_graph": STEPS_PER_GRAPH}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_steps = args.cpu_steps or max(16, min(args.steps * 4, 16000))
+        cpu_steps = args.cpu_steps or max(16, min(args.steps * 16, 32000))
         res = cpu_reference(1, cpu_steps, 16, args.atoms, seed)
         cpu_steps = int(round(res['ms_per_step'] and res['seconds'] / (res['ms_per_step'] * 1e-3)))
         line = {"impl": "reference", "metric": "mmvt_aggregate_anchor_ns_per_day", "value": res["value"], "unit": "anchor-ns/day",
@@ -281,8 +281,11 @@ def main() -> None:
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this very
+    # workload (profiles/r01_fused_step_ncu_full.txt: 260.2 MB read + 135.6 MB written); null otherwise
+    traffic = 395.8e6 if (A, args.atoms) == (128, N_ATOMS) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_step_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
+                "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback"}
 
@@ -333,7 +336,7 @@ def main() -> None:
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(1, args.cpu_steps or 16000, 16, args.atoms, seed)   # ~10 s at ~0.6 ms per anchor-step
+        cpu = cpu_reference(1, args.cpu_steps or 32000, 16, args.atoms, seed)   # ~12 s at ~0.38 ms per anchor-step
 
     if rank == 0:
         line = {"metric": "mmvt_aggregate_anchor_ns_per_day", "value": value, "unit": "anchor-ns/day", "n_gpus": world,
