@@ -16,6 +16,8 @@
  *       platforms/cuda/src/CudaSeekr2Kernels.cpp:391-595
  *   integrate{Mmvt,Elber}LangevinPart1/Part2, mmvtBounce
  *       platforms/cuda/src/kernels/langevin.cu:7-179
+ *   IntegrateMmvtLangevinMiddleStepKernel / IntegrateElberLangevinMiddleStepKernel (scheme MIDDLE)
+ *       openmmapi/include/Seekr2Kernels.h:115-172, platforms/cuda/src/kernels/langevinMiddle.cu:7-214
  *
  * Conventions
  *   - plain C, no C++/torch types; all pointers named d_* are CUDA device pointers, `stream`
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 1
+#define SEEKR2_B200_ABI_VERSION 2
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -82,6 +84,14 @@ enum {
 /* integrator kind */
 enum { SEEKR2_B200_KIND_LANGEVIN = 0, SEEKR2_B200_KIND_MMVT = 1, SEEKR2_B200_KIND_ELBER = 2 };
 
+/* discretisation of the Langevin equation.
+ *   LANGEVIN : {Mmvt,Elber}LangevinIntegrator       -- kick (v,F,noise) then drift (langevin.cu)
+ *   MIDDLE   : {Mmvt,Elber}LangevinMiddleIntegrator -- force kick, half drift, O step, half drift
+ *              (langevinMiddle.cu:7-101,104-196; host CudaSeekr2Kernels.cpp:725-915,1032-1173).
+ *              A bounce negates the velocity saved after the force kick (langevinMiddle.cu:41,
+ *              :202-214).  Fused single-launch step only in this release (no constraint passes).  */
+enum { SEEKR2_B200_SCHEME_LANGEVIN = 0, SEEKR2_B200_SCHEME_MIDDLE = 1 };
+
 /* boundary surface types: the typed form of the CustomCentroidBondForce expressions the
  * reference's examples use.  u is the surface function; the term contributed to
  * the force-group energy is  bitcode*step(k*u)  (STEP style) or  k*u  (RAW, the older style).   */
@@ -112,6 +122,7 @@ typedef struct seekr2_b200_config {
     int32_t precision;            /* SEEKR2_B200_SINGLE / MIXED / DOUBLE                           */
     int32_t variant;              /* SEEKR2_B200_VARIANT_*                                         */
     int32_t flags;                /* SEEKR2_B200_FLAG_*                                            */
+    int32_t scheme;               /* SEEKR2_B200_SCHEME_*                                          */
     int32_t device;               /* CUDA device ordinal; -1 = current device                      */
     int32_t num_anchors;          /* A: independent replicas of the system batched per launch      */
     int32_t num_atoms;            /* N                                                             */

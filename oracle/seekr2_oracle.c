@@ -102,7 +102,7 @@
 /* ---- oracle object ---------------------------------------------------------------------------- */
 
 typedef struct seekr2_oracle {
-    int kind, precision, variant, flags;
+    int kind, precision, variant, flags, scheme;
     int numAtoms, paddedNumAtoms;
     int numGroups;
     int* groupOffsets;
@@ -122,6 +122,7 @@ typedef struct seekr2_oracle {
     double srcValues[SEEKR2_B200_MAX_ELBER], destValues[SEEKR2_B200_MAX_ELBER]; /* vector<double>, -INFINITY = unsampled (CudaSeekr2Kernels.h:151-152) */
     /* scratch: posDelta + old state (the reference's oldPosq / oldVelm, CudaSeekr2Kernels.cpp:82-102) */
     void* posDelta;
+    void* oldDelta;                   /* LangevinMiddle (CudaSeekr2Kernels.cpp:630-643) */
     void* oldPosq;
     void* oldPosqCorrection;
     void* oldVelm;
@@ -138,7 +139,7 @@ static size_t mixed4_size(int precision) { return precision == SEEKR2_B200_SINGL
 void seekr2_oracle_destroy(seekr2_oracle* o) {
     if (!o) return;
     free(o->groupOffsets); free(o->groupAtoms); free(o->groupWeights); free(o->boundaries);
-    free(o->posDelta); free(o->oldPosq); free(o->oldPosqCorrection); free(o->oldVelm);
+    free(o->posDelta); free(o->oldDelta); free(o->oldPosq); free(o->oldPosqCorrection); free(o->oldVelm);
     free(o->startVelm); free(o->startForce); free(o->records);
     free(o);
 }
@@ -147,7 +148,7 @@ void seekr2_oracle_destroy(seekr2_oracle* o) {
 seekr2_oracle* seekr2_oracle_create(const seekr2_b200_config* cfg, int anchor) {
     if (!cfg || anchor < 0 || anchor >= cfg->num_anchors) return NULL;
     seekr2_oracle* o = (seekr2_oracle*) calloc(1, sizeof(seekr2_oracle));
-    o->kind = cfg->kind; o->precision = cfg->precision; o->variant = cfg->variant; o->flags = cfg->flags;
+    o->kind = cfg->kind; o->precision = cfg->precision; o->variant = cfg->variant; o->flags = cfg->flags; o->scheme = cfg->scheme;
     o->numAtoms = cfg->num_atoms; o->paddedNumAtoms = cfg->padded_num_atoms;
     o->anchor = anchor;
     o->numGroups = cfg->num_groups;
@@ -185,6 +186,7 @@ seekr2_oracle* seekr2_oracle_create(const seekr2_b200_config* cfg, int anchor) {
     o->st.previous_milestone = -1;
     size_t np = (size_t) cfg->padded_num_atoms;
     o->posDelta = calloc(np, mixed4_size(o->precision));
+    o->oldDelta = calloc(np, mixed4_size(o->precision));
     o->oldPosq = calloc(np, real4_size(o->precision));
     o->oldPosqCorrection = calloc(np, real4_size(o->precision));
     o->oldVelm = calloc(np, mixed4_size(o->precision));
@@ -309,8 +311,36 @@ void seekr2_oracle_set_time(seekr2_oracle* o, double time, int64_t stepCount) { 
 
 /* ---- the steps ------------------------------------------------------------------------------ */
 
+/* LangevinMiddle: Part1, (velocity constraints), Part2, (constraints), Part3
+   (CudaSeekr2Kernels.cpp:762-802; Elber twin :1057-1096) */
+static void langevin_middle_parts(seekr2_oracle* o, void* posq, void* corr, void* velm, const long long* force,
+                                  const float* random4, unsigned int randomIndex, int saveOld) {
+    const double p2[2] = { o->params[0], o->params[2] };   /* {vscale, noisescale} (:741-747) */
+    switch (o->precision) {
+    case SEEKR2_B200_SINGLE:
+        middle_part1_s(o->numAtoms, o->paddedNumAtoms, (mixed4_s*) velm, force, o->stepSize);
+        middle_part2_s(o->numAtoms, (mixed4_s*) velm, (mixed4_s*) o->posDelta, (mixed4_s*) o->oldDelta, p2, o->stepSize, saveOld ? (mixed4_s*) o->oldVelm : NULL, random4, randomIndex);
+        middle_part3_s(o->numAtoms, (real4_s*) posq, (mixed4_s*) velm, (const mixed4_s*) o->posDelta, (const mixed4_s*) o->oldDelta, o->stepSize, saveOld ? (real4_s*) o->oldPosq : NULL, NULL);
+        break;
+    case SEEKR2_B200_MIXED:
+        middle_part1_m(o->numAtoms, o->paddedNumAtoms, (mixed4_m*) velm, force, o->stepSize);
+        middle_part2_m(o->numAtoms, (mixed4_m*) velm, (mixed4_m*) o->posDelta, (mixed4_m*) o->oldDelta, p2, o->stepSize, saveOld ? (mixed4_m*) o->oldVelm : NULL, random4, randomIndex);
+        middle_part3_m(o->numAtoms, (real4_m*) posq, (mixed4_m*) velm, (const mixed4_m*) o->posDelta, (const mixed4_m*) o->oldDelta, o->stepSize, saveOld ? (real4_m*) o->oldPosq : NULL, (real4_m*) corr);
+        break;
+    default:
+        middle_part1_d(o->numAtoms, o->paddedNumAtoms, (mixed4_d*) velm, force, o->stepSize);
+        middle_part2_d(o->numAtoms, (mixed4_d*) velm, (mixed4_d*) o->posDelta, (mixed4_d*) o->oldDelta, p2, o->stepSize, saveOld ? (mixed4_d*) o->oldVelm : NULL, random4, randomIndex);
+        middle_part3_d(o->numAtoms, (real4_d*) posq, (mixed4_d*) velm, (const mixed4_d*) o->posDelta, (const mixed4_d*) o->oldDelta, o->stepSize, saveOld ? (real4_d*) o->oldPosq : NULL, NULL);
+        break;
+    }
+}
+
 static void langevin_two_parts(seekr2_oracle* o, void* posq, void* corr, void* velm, const long long* force,
                                const float* random4, unsigned int randomIndex, int saveOld) {
+    if (o->scheme == SEEKR2_B200_SCHEME_MIDDLE) {
+        langevin_middle_parts(o, posq, corr, velm, force, random4, randomIndex, saveOld);
+        return;
+    }
     seekr2_oracle_part1(o, velm, force, o->posDelta, random4, randomIndex);
     /* applyConstraints (CudaSeekr2Kernels.cpp:227): identity, the harness systems have none */
     seekr2_oracle_part2(o, posq, corr, o->posDelta, velm, saveOld ? o->oldPosq : NULL, saveOld ? o->oldVelm : NULL);

@@ -11,9 +11,13 @@ from ._lib import (  # noqa: F401
 )
 from .system import System, HarmonicBondForce, TetherForce, CustomCentroidBondForce  # noqa: F401
 from .context import Context, State, BOLTZ  # noqa: F401
-from .integrators import MmvtLangevinIntegrator, ElberLangevinIntegrator, LangevinIntegrator  # noqa: F401
+from .integrators import (  # noqa: F401
+    MmvtLangevinIntegrator, ElberLangevinIntegrator, LangevinIntegrator,
+    MmvtLangevinMiddleIntegrator, ElberLangevinMiddleIntegrator, LangevinMiddleIntegrator,
+)
 
 __all__ = [
     "Seekr2Error", "System", "HarmonicBondForce", "TetherForce", "CustomCentroidBondForce", "Context", "State",
     "MmvtLangevinIntegrator", "ElberLangevinIntegrator", "LangevinIntegrator", "BOLTZ",
+    "MmvtLangevinMiddleIntegrator", "ElberLangevinMiddleIntegrator", "LangevinMiddleIntegrator",
 ]

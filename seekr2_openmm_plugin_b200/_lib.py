@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseekr2_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -25,6 +25,7 @@ SINGLE, MIXED, DOUBLE = 0, 1, 2
 VARIANT_CUDA, VARIANT_REFERENCE = 0, 1
 FLAG_RESTORE_CORRECTION = 1
 KIND_LANGEVIN, KIND_MMVT, KIND_ELBER = 0, 1, 2
+SCHEME_LANGEVIN, SCHEME_MIDDLE = 0, 1
 CV_SPHERE_PAIR, CV_SPHERE_FIXED, CV_PLANE = 0, 1, 2
 STYLE_STEP, STYLE_RAW = 0, 1
 REC_MMVT, REC_ELBER_SRC, REC_ELBER_DEST, REC_ELBER_DEST_STAR = 0, 1, 2, 3
@@ -51,7 +52,7 @@ class Boundary(C.Structure):
 class Config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("kind", C.c_int32), ("precision", C.c_int32), ("variant", C.c_int32),
-        ("flags", C.c_int32), ("device", C.c_int32), ("num_anchors", C.c_int32), ("num_atoms", C.c_int32),
+        ("flags", C.c_int32), ("scheme", C.c_int32), ("device", C.c_int32), ("num_anchors", C.c_int32), ("num_atoms", C.c_int32),
         ("padded_num_atoms", C.c_int32),
         ("num_groups", C.c_int32), ("group_offsets", C.POINTER(C.c_int32)), ("group_atoms", C.POINTER(C.c_int32)),
         ("group_weights", C.POINTER(C.c_double)),

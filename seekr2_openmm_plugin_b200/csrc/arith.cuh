@@ -147,6 +147,10 @@ template <int P> struct StepParams {
     typename Prec<P>::mixed noisescale;  // params[NoiseScale]
     typename Prec<P>::mixed dt;          // dt[0].y
     double inv_dt;                       // 1.0 / dt[0].y, always double (langevin.cu:71)
+    // LangevinMiddle scheme (langevinMiddle.cu:11,37,73)
+    typename Prec<P>::mixed fs_mid;      // dt[0].y / 2^32
+    typename Prec<P>::mixed halfdt;      // 0.5f * dt[0].y
+    typename Prec<P>::mixed inv_dt_m;    // 1 / dt[0].y in MIXED precision
 };
 
 template <int P> struct Vec3M { typename Prec<P>::mixed x, y, z; };
@@ -194,6 +198,55 @@ __device__ __forceinline__ void drift(const StepParams<P>& p, const typename Pre
         xn.x = __dadd_rn(x.x, d.x); xn.y = __dadd_rn(x.y, d.y); xn.z = __dadd_rn(x.z, d.z); xn.w = x.w;
         cn = c;
         v.x = __dmul_rn(p.inv_dt, d.x); v.y = __dmul_rn(p.inv_dt, d.y); v.z = __dmul_rn(p.inv_dt, d.z);
+    }
+}
+
+// ---- LangevinMiddle scheme (langevinMiddle.cu), fma placement as nvcc emits for the reference ------
+// Part1 (:7-21): v1 = fma(fs*w, (mixed)F, v)
+template <int P>
+__device__ __forceinline__ void middle_kick(const StepParams<P>& p, typename Prec<P>::mixed4& v, long long fx,
+                                            long long fy, long long fz) {
+    using M = typename Prec<P>::mixed;
+    const M fw = mul_rn(p.fs_mid, v.w);
+    v.x = fma_rn(fw, from_ll<M>(fx), v.x);
+    v.y = fma_rn(fw, from_ll<M>(fy), v.y);
+    v.z = fma_rn(fw, from_ll<M>(fz), v.z);
+}
+// Part2 (:28-61): v2 = fma(vs, v1, (ns*SQRT(w))*R); delta = fma(h, v1, h*v2).  v: v1 in, v2 out.
+template <int P>
+__device__ __forceinline__ void middle_ou_drift(const StepParams<P>& p, typename Prec<P>::mixed4& v, const float4& r,
+                                                Vec3M<P>& delta) {
+    using M = typename Prec<P>::mixed;
+    const M b = mul_rn(p.noisescale, sqrt_inv_mass<P>(v.w));
+    const M nx = fma_rn(p.vscale, v.x, mul_rn(b, (M) r.x));
+    const M ny = fma_rn(p.vscale, v.y, mul_rn(b, (M) r.y));
+    const M nz = fma_rn(p.vscale, v.z, mul_rn(b, (M) r.z));
+    delta.x = fma_rn(p.halfdt, v.x, mul_rn(p.halfdt, nx));
+    delta.y = fma_rn(p.halfdt, v.y, mul_rn(p.halfdt, ny));
+    delta.z = fma_rn(p.halfdt, v.z, mul_rn(p.halfdt, nz));
+    v.x = nx; v.y = ny; v.z = nz;
+}
+// Part3 (:68-101): v3 = fma(invDt, delta - oldDelta, v2); X = delta + (x + corr); split.
+template <int P>
+__device__ __forceinline__ void middle_finish(const StepParams<P>& p, const typename Prec<P>::real4& x,
+                                              const typename Prec<P>::real4& c, const Vec3M<P>& d, const Vec3M<P>& d_old,
+                                              typename Prec<P>::real4& xn, typename Prec<P>::real4& cn,
+                                              typename Prec<P>::mixed4& v) {
+    v.x = fma_rn(p.inv_dt_m, sub_rn(d.x, d_old.x), v.x);
+    v.y = fma_rn(p.inv_dt_m, sub_rn(d.y, d_old.y), v.y);
+    v.z = fma_rn(p.inv_dt_m, sub_rn(d.z, d_old.z), v.z);
+    if constexpr (P == MIXED) {
+        const double X = __dadd_rn(d.x, __dadd_rn((double) x.x, (double) c.x));
+        const double Y = __dadd_rn(d.y, __dadd_rn((double) x.y, (double) c.y));
+        const double Z = __dadd_rn(d.z, __dadd_rn((double) x.z, (double) c.z));
+        xn.x = __double2float_rn(X); xn.y = __double2float_rn(Y); xn.z = __double2float_rn(Z); xn.w = x.w;
+        cn.x = __double2float_rn(__dsub_rn(X, (double) xn.x));
+        cn.y = __double2float_rn(__dsub_rn(Y, (double) xn.y));
+        cn.z = __double2float_rn(__dsub_rn(Z, (double) xn.z));
+        cn.w = 0.0f;
+    } else {
+        xn.x = add_rn(d.x, x.x); xn.y = add_rn(d.y, x.y); xn.z = add_rn(d.z, x.z); xn.w = x.w;
+        cn = c;
     }
 }
 

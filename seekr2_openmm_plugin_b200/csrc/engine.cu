@@ -115,6 +115,9 @@ template <int P> StepParams<P> step_params(const seekr2_b200_engine* h) {
     p.noisescale = (M) h->params[2];
     p.dt = (M) h->step_size;
     p.inv_dt = 1.0 / (double) p.dt;
+    p.fs_mid = p.dt / (M) 4294967296.0;      // langevinMiddle.cu:11
+    p.halfdt = 0.5f * p.dt;                  // :37
+    p.inv_dt_m = 1 / p.dt;                   // :73 (mixed precision, unlike langevin.cu:71)
     return p;
 }
 
@@ -142,19 +145,26 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
     return SEEKR2_B200_OK;
 }
 
-template <int P, int KIND> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
     const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
-    fused_step_kernel<P, KIND><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa);
+    fused_step_kernel<P, KIND, SCHEME><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }
 
 template <int P> int launch_fused_kind(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+    if (h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE) {
+        switch (h->cfg.kind) {
+        case SEEKR2_B200_KIND_MMVT: return launch_fused<P, SEEKR2_B200_KIND_MMVT, SEEKR2_B200_SCHEME_MIDDLE>(h, b, ri, s);
+        case SEEKR2_B200_KIND_ELBER: return launch_fused<P, SEEKR2_B200_KIND_ELBER, SEEKR2_B200_SCHEME_MIDDLE>(h, b, ri, s);
+        default: return launch_fused<P, SEEKR2_B200_KIND_LANGEVIN, SEEKR2_B200_SCHEME_MIDDLE>(h, b, ri, s);
+        }
+    }
     switch (h->cfg.kind) {
-    case SEEKR2_B200_KIND_MMVT: return launch_fused<P, SEEKR2_B200_KIND_MMVT>(h, b, ri, s);
-    case SEEKR2_B200_KIND_ELBER: return launch_fused<P, SEEKR2_B200_KIND_ELBER>(h, b, ri, s);
-    default: return launch_fused<P, SEEKR2_B200_KIND_LANGEVIN>(h, b, ri, s);
+    case SEEKR2_B200_KIND_MMVT: return launch_fused<P, SEEKR2_B200_KIND_MMVT, SEEKR2_B200_SCHEME_LANGEVIN>(h, b, ri, s);
+    case SEEKR2_B200_KIND_ELBER: return launch_fused<P, SEEKR2_B200_KIND_ELBER, SEEKR2_B200_SCHEME_LANGEVIN>(h, b, ri, s);
+    default: return launch_fused<P, SEEKR2_B200_KIND_LANGEVIN, SEEKR2_B200_SCHEME_LANGEVIN>(h, b, ri, s);
     }
 }
 
@@ -214,6 +224,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     if (cfg->abi_version != SEEKR2_B200_ABI_VERSION) return fail(SEEKR2_B200_ERR_INVALID, "ABI version mismatch: header %d, caller %d", SEEKR2_B200_ABI_VERSION, cfg->abi_version);
     if (cfg->precision < SINGLE || cfg->precision > DOUBLE) return fail(SEEKR2_B200_ERR_INVALID, "bad precision %d", cfg->precision);
     if (cfg->kind < SEEKR2_B200_KIND_LANGEVIN || cfg->kind > SEEKR2_B200_KIND_ELBER) return fail(SEEKR2_B200_ERR_INVALID, "bad integrator kind %d", cfg->kind);
+    if (cfg->scheme != SEEKR2_B200_SCHEME_LANGEVIN && cfg->scheme != SEEKR2_B200_SCHEME_MIDDLE) return fail(SEEKR2_B200_ERR_INVALID, "bad scheme %d", cfg->scheme);
     if (cfg->variant != SEEKR2_B200_VARIANT_CUDA && cfg->variant != SEEKR2_B200_VARIANT_REFERENCE) return fail(SEEKR2_B200_ERR_INVALID, "bad variant %d", cfg->variant);
     if (cfg->num_anchors < 1 || cfg->num_anchors > 65535) return fail(SEEKR2_B200_ERR_INVALID, "num_anchors must be in [1, 65535]");
     if (cfg->num_atoms < 1 || cfg->padded_num_atoms < cfg->num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "bad atom counts %d / %d", cfg->num_atoms, cfg->padded_num_atoms);
@@ -435,6 +446,7 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
 
 int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index, void* stream) {
     if (int rc = check_bufs(h, bufs, true, true)) return rc;
+    if (h->cfg.scheme != SEEKR2_B200_SCHEME_LANGEVIN) return fail(SEEKR2_B200_ERR_INVALID, "the LangevinMiddle scheme has no multi-pass (constraint) path yet: use seekr2_b200_step");
     if (h->cfg.variant == SEEKR2_B200_VARIANT_REFERENCE && h->cfg.kind == SEEKR2_B200_KIND_MMVT && !bufs->d_old_velm)
         return fail(SEEKR2_B200_ERR_INVALID, "VARIANT_REFERENCE two-pass MMVT needs d_old_velm");
     DeviceGuard guard(h->device);
@@ -445,6 +457,7 @@ int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
 
 int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream) {
     if (int rc = check_bufs(h, bufs, false, true)) return rc;
+    if (h->cfg.scheme != SEEKR2_B200_SCHEME_LANGEVIN) return fail(SEEKR2_B200_ERR_INVALID, "the LangevinMiddle scheme has no multi-pass (constraint) path yet: use seekr2_b200_step");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
     h->slab_valid = false;   // the two-pass path does not maintain the slab

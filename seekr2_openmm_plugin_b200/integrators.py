@@ -29,6 +29,7 @@ def _i32_array(values: Sequence[int]):
 
 class _B200LangevinBase:
     KIND = L.KIND_LANGEVIN
+    SCHEME = L.SCHEME_LANGEVIN
     KERNEL_NAME = "IntegrateLangevinStep"
 
     def __init__(self, temperature: float, frictionCoeff: float, stepSize: float, fileName: str = ""):
@@ -104,6 +105,7 @@ class _B200LangevinBase:
         cfg.precision = precision
         cfg.variant = self.variant
         cfg.flags = self.flags
+        cfg.scheme = self.SCHEME
         cfg.device = device
         cfg.num_anchors = num_anchors
         cfg.num_atoms = n
@@ -397,6 +399,19 @@ class MmvtLangevinIntegrator(_B200LangevinBase):
                 L.check(L.lib.seekr2_b200_write_statistics(name.encode(), C.byref(st), _i32_array(labels), len(labels)))
 
 
+class LangevinMiddleIntegrator(_B200LangevinBase):
+    """Plain LangevinMiddle step (comparator for the Middle MMVT step)."""
+    SCHEME = L.SCHEME_MIDDLE
+
+
+class MmvtLangevinMiddleIntegrator(MmvtLangevinIntegrator):
+    """``Seekr2Plugin::MmvtLangevinMiddleIntegrator`` -- what the reference's examples instantiate
+    (mmvt_demonstration3_tryp_benz_spherical.py:59).  Kernel: langevinMiddle.cu:7-101; a bounce negates
+    the velocity saved after the force kick (:41, :202-214).  Fused single-launch step only."""
+    SCHEME = L.SCHEME_MIDDLE
+    KERNEL_NAME = "IntegrateMmvtLangevinMiddleStep"     # Seekr2Kernels.h:117-119
+
+
 class ElberLangevinIntegrator(_B200LangevinBase):
     """``Seekr2Plugin::ElberLangevinIntegrator`` (ElberLangevinIntegrator.h:60-232)."""
     KIND = L.KIND_ELBER
@@ -450,3 +465,10 @@ class ElberLangevinIntegrator(_B200LangevinBase):
         cfg.num_dest, cfg.dest_groups = len(self.destMilestoneGroups), dst
         cfg.end_on_src_milestone = 1 if self.endOnSrcMilestone else 0
         cfg.crossing_counter0 = cc
+
+
+class ElberLangevinMiddleIntegrator(ElberLangevinIntegrator):
+    """``Seekr2Plugin::ElberLangevinMiddleIntegrator`` (langevinMiddle.cu:104-196; host logic identical to
+    the non-Middle Elber kernel, CudaSeekr2Kernels.cpp:1098-1173)."""
+    SCHEME = L.SCHEME_MIDDLE
+    KERNEL_NAME = "IntegrateElberLangevinMiddleStep"    # Seekr2Kernels.h:148-150

@@ -37,6 +37,7 @@ def cases():
     for prec in (L.SINGLE, L.MIXED, L.DOUBLE):
         out[f"toy_mmvt_{NAMES[prec]}"] = (H.toy_system, lambda syn: H.make_mmvt_integrator(syn, ""), prec, 100000, H.SEED_BASE + 1)
     out["toy_mmvt_mixed_reference_variant"] = (H.toy_system, lambda syn: H.make_mmvt_integrator(syn, "", "reference"), L.MIXED, 100000, H.SEED_BASE + 1)
+    out["toy_mmvt_middle_mixed"] = (H.toy_system, lambda syn: H.make_mmvt_integrator(syn, "", middle=True), L.MIXED, 100000, H.SEED_BASE + 1)
     out["ballistic_corner_mixed"] = (lambda: S.ballistic_toy(extra_plane=True), lambda syn: H.make_mmvt_integrator(syn, ""), L.MIXED, 400, None)
     out["ballistic_rawstyle_double"] = (lambda: S.ballistic_toy(raw_style=True), lambda syn: H.make_mmvt_integrator(syn, ""), L.DOUBLE, 200, None)
 
@@ -55,6 +56,15 @@ def cases():
             integ.setCrossingCounter(5)
             return integ
         out[f"elber_ballistic_end{int(end)}_mixed"] = (elber, einteg, L.MIXED, 120, None)
+
+        def elber_m(end=end):
+            return S.elber_ballistic(end, middle=True)[0]
+
+        def einteg_m(syn, end=end):
+            integ = S.elber_ballistic(end, middle=True)[1]
+            integ.setCrossingCounter(5)
+            return integ
+        out[f"elber_middle_ballistic_end{int(end)}_mixed"] = (elber_m, einteg_m, L.MIXED, 120, None)
     return out
 
 

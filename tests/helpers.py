@@ -185,8 +185,9 @@ def place_pair_distance(syn: Synthetic, host: List[int], guest: List[int], dista
 
 # ---- running both implementations ---------------------------------------------------------------------
 
-def make_mmvt_integrator(syn: Synthetic, path: str = "", variant: str = "cuda") -> "s2.MmvtLangevinIntegrator":
-    integ = s2.MmvtLangevinIntegrator(syn.temperature, syn.friction, syn.dt, path)
+def make_mmvt_integrator(syn: Synthetic, path: str = "", variant: str = "cuda", middle: bool = False) -> "s2.MmvtLangevinIntegrator":
+    cls = s2.MmvtLangevinMiddleIntegrator if middle else s2.MmvtLangevinIntegrator
+    integ = cls(syn.temperature, syn.friction, syn.dt, path)
     for g in syn.milestone_groups:
         integ.addMilestoneGroup(g)
     integ.setVariant(variant)

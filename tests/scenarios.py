@@ -40,7 +40,7 @@ def ballistic_toy(extra_plane: bool = False, raw_style: bool = False, speed: flo
     return syn
 
 
-def elber_ballistic(end_on_src: bool, speed: float = 0.5, start: float = 0.95, dt: float = 0.01):
+def elber_ballistic(end_on_src: bool, speed: float = 0.5, start: float = 0.95, dt: float = 0.01, middle: bool = False):
     """One particle moving along +x; source milestone sphere r = 1.0 (force group 1), destination
     milestones r = 0.9 (group 2) and r = 1.1 (group 3), all centred at (1.2, 1.2, 1.2)."""
     system = s2.System()
@@ -55,7 +55,7 @@ def elber_ballistic(end_on_src: bool, speed: float = 0.5, start: float = 0.95, d
         system.addForce(f)
     syn = H.Synthetic(system, np.array([[1.2 + start, 1.2, 1.2]]), np.array([[speed, 0.0, 0.0]]), np.array([39.9]),
                       None, [], 0.0, dt, temperature=0.0, friction=0.0)
-    integ = s2.ElberLangevinIntegrator(0.0, 0.0, dt, "")
+    integ = (s2.ElberLangevinMiddleIntegrator if middle else s2.ElberLangevinIntegrator)(0.0, 0.0, dt, "")
     integ.addSrcMilestoneGroup(1)
     integ.addDestMilestoneGroup(2)
     integ.addDestMilestoneGroup(3)
