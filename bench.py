@@ -152,6 +152,7 @@ def main() -> None:
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-box", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -306,6 +307,36 @@ def main() -> None:
     del ctx1, integ1
     A = A_saved
 
+    # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---
+    box = None
+    if not args.no_box:
+        import helpers as Hb
+        nb, Ab = 100000, max(2, min(32, args.anchors // 4))
+        synb = Hb.pair_sphere_system(nb, [i for i in REC], [i for i in LIG], 1.1, 1.3, seed + 5, dt=0.002, tether_k=0.0,
+                                     extra_planes=True, plane_group=list(range(5000, 5064)))
+        Hb.place_pair_distance(synb, REC, LIG, 1.2)
+        integ_b = Hb.make_mmvt_integrator(synb, "")
+        integ_b.setRandomNumberSeed(seed + 77 + rank)
+        integ_b.rngAnchorBase = rank * Ab
+        integ_b.ringCapacity = 1 << 14
+        integ_b.setUseGraph(True, STEPS_PER_GRAPH)
+        ctx_b = s2.Context(synb.system, integ_b, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=Ab)
+        ctx_b.setPositions(synb.positions)
+        ctx_b.setVelocities(synb.velocities)
+        b_steps = max(STEPS_PER_GRAPH, args.steps // 4 // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
+        tb, kb, nbl, _ = timed_run(ctx_b, integ_b, b_steps, W)
+        if world > 1:
+            t = torch.tensor([tb], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tb = float(t.item())
+        per_launch = kb * 1e-3 / nbl
+        box = {"workload": f"C5 box: {nb} atoms, {Ab} anchors per GPU, 2 centroid-pair spheres + 4 axis planes, dt 2 fs, mixed",
+               "anchor_ns_per_day": b_steps / (tb * 1e-3) * 0.002e-3 * 86400.0 * Ab * world,
+               "us_per_launch": per_launch * 1e6,
+               "achieved_gbs": Ab * nb * BYTES_PER_ATOM_STEP / per_launch / 1e9,
+               "frac_of_hbm_peak": Ab * nb * BYTES_PER_ATOM_STEP / per_launch / 1e9 / peak}
+        del ctx_b, integ_b
+
     # ---- end to end through the public API with HOST force buffers ------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -346,7 +377,7 @@ def main() -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "ns_per_day_per_anchor": value / (A * world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches + fills, "roofline": roofline, "cpu_baseline": cpu,
-                "mmvt_over_plain_langevin": mmvt_over_langevin, "single_anchor_per_gpu": single_anchor,
+                "mmvt_over_plain_langevin": mmvt_over_langevin, "single_anchor_per_gpu": single_anchor, "box_100k": box,
                 "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
                 "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
         print(json.dumps(line))

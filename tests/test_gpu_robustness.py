@@ -1,0 +1,130 @@
+"""Robustness of the engine's device-resident state: external state changes between steps, ring overflow,
+parameter changes mid-run, statistics files, long-run statistical agreement of the in-kernel RNG path."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+import scenarios as S
+from helpers import L, s2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_set_positions_mid_run_resyncs_group_slab(cuda_device):
+    """Context.setPositions / setVelocities between steps (what a user or a barostat does): the engine
+    re-gathers the boundary-group slab, and the continuation equals an oracle run restarted from that state."""
+    host, guest = list(range(0, 11)), list(range(11, 20))
+    syn = H.pair_sphere_system(500, host, guest, 0.185, 0.195, H.SEED_BASE + 13, tether_k=500.0)
+    H.place_pair_distance(syn, host, guest, 0.19)
+    pool = H.gaussian_pool(31, 200 * 512)
+    integ = H.make_mmvt_integrator(syn, "")
+    hb = H.make_host_buffers(L.MIXED, syn.positions, syn.velocities, syn.masses)
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    H.upload(ctx, [hb])
+    ctx.setRandomPool(pool)
+    integ.step(100)
+    mid = H.download(ctx)
+    # move the guest group by hand (public API) and continue
+    x = ctx.positions_host()[0]
+    x[guest] += np.array([0.001, -0.0005, 0.0])
+    ctx.setPositions(x)
+    ctx.setVelocities(ctx.velocities_host()[0] * 0.5)
+    restart = H.download(ctx)
+    integ.step(100)
+    got = H.download(ctx)
+    # a fresh oracle started from the modified state (fresh bookkeeping, so only the atoms' evolution is
+    # compared; its step-0 check is skipped by giving it the engine's step count)
+    o = H.oracle_for(H.make_mmvt_integrator(syn, ""), syn.system, L.MIXED)
+    o.lib.seekr2_oracle_set_time(o.h, integ.getAnchorState(0).time - 100 * syn.dt, 100)
+    ob = restart.copy()
+    x0 = hb.posq.copy()
+    assert o.run(100, ob.posq, ob.corr, ob.velm, ob.force, pool, 100 * 512, x0, 500.0) == 0
+    H.assert_state_equal(ob, got, 500, "continuation after setPositions")
+    assert (mid.posq[:500] != restart.posq[:500]).any()
+
+
+def test_ring_overflow_is_reported_not_silent(cuda_device):
+    syn = S.ballistic_toy(speed=5.0, dt=0.01)          # bounces every ~4 steps
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.ringCapacity = 8
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    ctx.setPositions(syn.positions)
+    ctx.setVelocities(syn.velocities)
+    with pytest.raises(s2.Seekr2Error) as err:
+        integ.step(400)
+    assert err.value.code == L.ERR_RING_OVERFLOW
+    # counters on the device are still exact
+    assert integ.getAnchorState(0).bounce_counter > 8
+    integ.step(8)                                       # and the engine keeps working afterwards
+
+
+def test_parameter_change_mid_run_and_statistics_file(cuda_device, tmp_path):
+    """T / gamma / dt setters take effect at the next step (CudaSeekr2Kernels.cpp:188-203); the statistics
+    file matches the oracle's byte for byte."""
+    syn = H.toy_system()
+    pool = H.gaussian_pool(17, 4000 * 32)
+    stats_gpu, stats_cpu = str(tmp_path / "gpu_stats.txt"), str(tmp_path / "cpu_stats.txt")
+    integ = H.make_mmvt_integrator(syn, str(tmp_path / "gpu.txt"))
+    integ.setSaveStatisticsFileName(stats_gpu)
+    hb = H.make_host_buffers(L.MIXED, syn.positions, syn.velocities, syn.masses)
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    H.upload(ctx, [hb])
+    ctx.setRandomPool(pool)
+    o = H.oracle_for(H.make_mmvt_integrator(syn, ""), syn.system, L.MIXED)
+    ob = hb.copy()
+    integ.step(2000)
+    assert o.run(2000, ob.posq, ob.corr, ob.velm, ob.force, pool, 0, None, 0.0) == 0
+    integ.setTemperature(350.0); integ.setFriction(2.0); integ.setStepSize(0.001)
+    o.set_params(350.0, 2.0, 0.001)
+    integ.step(2000)
+    assert o.run(2000, ob.posq, ob.corr, ob.velm, ob.force, pool, 2000 * 32, None, 0.0) == 0
+    H.assert_state_equal(ob, H.download(ctx), 1)
+    assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0))
+    assert len(o.records()) > 0
+    o.write_statistics(stats_cpu, syn.milestone_groups)
+    assert open(stats_gpu).read() == open(stats_cpu).read()
+
+
+def test_long_run_statistics_in_kernel_rng_vs_oracle(cuda_device):
+    """North star: long-run MMVT statistics agree within statistical error when the random numbers differ.
+    256 replicas of the toy system with the in-kernel Philox generator vs 16 oracle replicas with the
+    host-generated pool: bounce rate per milestone and mean incubation times R_i / N_ij."""
+    syn = H.toy_system()
+    steps = 40000
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.setRandomNumberSeed(2024)
+    integ.setUseGraph(True, 200)
+    integ.ringCapacity = 4096
+    A = 256
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
+    ctx.setPositions(syn.positions)
+    ctx.setVelocitiesToTemperature(300.0, 5)
+    integ.step(steps)
+    g_n = np.zeros(2); g_t = 0.0; g_r = np.zeros(2); g_nij = np.zeros(2)
+    for a in range(A):
+        st = integ.getAnchorState(a)
+        g_n += np.array(st.N_alpha_beta[:2]); g_t += st.T_alpha
+        g_r += np.array(st.Ri_alpha[:2]); g_nij += np.array([st.Nij_alpha[0 * L.MAX_MILESTONES + 1], st.Nij_alpha[1 * L.MAX_MILESTONES + 0]])
+    c_n = np.zeros(2); c_t = 0.0; c_r = np.zeros(2); c_nij = np.zeros(2)
+    R = 16
+    rng = np.random.default_rng(1)
+    for r in range(R):
+        o = H.oracle_for(H.make_mmvt_integrator(syn, ""), syn.system, L.MIXED)
+        vel = rng.standard_normal((1, 3)) * math.sqrt(s2.BOLTZ * 300.0 / 39.9)
+        hb = H.make_host_buffers(L.MIXED, syn.positions, vel, syn.masses)
+        pool = np.zeros((steps * 32, 4), dtype=np.float32)
+        pool[:, :3] = rng.standard_normal((steps * 32, 3)).astype(np.float32)
+        assert o.run(steps, hb.posq, hb.corr, hb.velm, hb.force, pool, 0, None, 0.0) == 0
+        st = o.state()
+        c_n += np.array(st.N_alpha_beta[:2]); c_t += st.T_alpha
+        c_r += np.array(st.Ri_alpha[:2]); c_nij += np.array([st.Nij_alpha[0 * L.MAX_MILESTONES + 1], st.Nij_alpha[1 * L.MAX_MILESTONES + 0]])
+    assert c_n.min() > 150 and g_n.min() > 2000
+    for i in range(2):
+        rate_g, rate_c = g_n[i] / g_t, c_n[i] / c_t
+        sigma = rate_c / math.sqrt(c_n[i]) + rate_g / math.sqrt(g_n[i])      # Poisson counting error
+        assert abs(rate_g - rate_c) < 5 * sigma, (i, rate_g, rate_c, sigma)
+        inc_g, inc_c = g_r[i] / g_nij[i], c_r[i] / c_nij[i]                  # mean incubation time before a switch
+        assert abs(inc_g - inc_c) < 0.25 * inc_c, (i, inc_g, inc_c)
