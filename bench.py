@@ -45,8 +45,7 @@ def ns_per_day(steps_per_s: float) -> float:
 
 
 def build_workload(num_anchors: int, n_atoms: int, seed: int):
-    import helpers as H
-    from helpers import s2
+    from seekr2_openmm_plugin_b200 import synthetic as H
     rec = [i for i in REC if i < n_atoms] or list(range(0, 11))
     lig = [i for i in LIG if i < n_atoms] or list(range(11, 20))
     syn = H.pair_sphere_system(n_atoms, rec, lig, 1.1, 1.3, seed, dt=DT_PS, tether_k=0.0)
@@ -107,7 +106,7 @@ class ClockSampler:
 def cpu_reference(num_anchors_per_thread: int, steps: int, warmup: int, n_atoms: int, seed: int) -> dict:
     """The reference's CPU path (oracle port of the Reference platform, double precision,
     VARIANT_REFERENCE incl. its three per-step copies) on all host cores, one anchor per thread."""
-    import helpers as H
+    import helpers as H                                         # tests/helpers.py: the ONLY place bench.py loads oracle/
     from helpers import L, s2
     cores = len(os.sched_getaffinity(0))
     syn, positions, forces, _ = build_workload(cores, n_atoms, seed)
@@ -183,9 +182,10 @@ def main() -> None:
         return
 
     import torch
-    import helpers as H
-    from helpers import L, s2
     import torch.distributed as dist
+    import seekr2_openmm_plugin_b200 as s2                     # the product: nothing from oracle/ on this arm
+    from seekr2_openmm_plugin_b200 import _lib as L
+    from seekr2_openmm_plugin_b200 import synthetic as H
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -310,7 +310,7 @@ def main() -> None:
     # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---
     box = None
     if not args.no_box:
-        import helpers as Hb
+        Hb = H
         nb, Ab = 100000, max(2, min(32, args.anchors // 4))
         synb = Hb.pair_sphere_system(nb, [i for i in REC], [i for i in LIG], 1.1, 1.3, seed + 5, dt=0.002, tether_k=0.0,
                                      extra_planes=True, plane_group=list(range(5000, 5064)))

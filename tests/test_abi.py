@@ -81,3 +81,28 @@ def test_no_cpu_fallback_without_gpu():
     syn = H.toy_system()
     with pytest.raises(L.Seekr2Error):
         H.s2.Context(syn.system, H.make_mmvt_integrator(syn, ""), {"CudaPrecision": "mixed"})
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: importing the package, building a workload and lowering a
+    configuration must not load it (bench.py's GPU arm relies on this)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, importlib.abc
+        class Guard(importlib.abc.MetaPathFinder):
+            def find_spec(self, name, path, target=None):
+                if name == 'oracle' or name.startswith('oracle.'):
+                    raise ImportError('oracle imported by the product path')
+        sys.meta_path.insert(0, Guard())
+        sys.path.insert(0, %r)
+        import seekr2_openmm_plugin_b200 as s2
+        from seekr2_openmm_plugin_b200 import synthetic, multi, _lib
+        import bench
+        syn, pos, f, sh = bench.build_workload(2, 300, 1)
+        integ = synthetic.make_mmvt_integrator(syn, '')
+        cfg = integ.makeConfig(syn.system, _lib.MIXED, 2)
+        assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)
+        print('clean')
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-2000:]
