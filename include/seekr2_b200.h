@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 2
+#define SEEKR2_B200_ABI_VERSION 3
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -89,7 +89,7 @@ enum { SEEKR2_B200_KIND_LANGEVIN = 0, SEEKR2_B200_KIND_MMVT = 1, SEEKR2_B200_KIN
  *   MIDDLE   : {Mmvt,Elber}LangevinMiddleIntegrator -- force kick, half drift, O step, half drift
  *              (langevinMiddle.cu:7-101,104-196; host CudaSeekr2Kernels.cpp:725-915,1032-1173).
  *              A bounce negates the velocity saved after the force kick (langevinMiddle.cu:41,
- *              :202-214).  Fused single-launch step only in this release (no constraint passes).  */
+ *              :202-214).  Fused: seekr2_b200_step.  With constraints: kick / middle_drift / finish.       */
 enum { SEEKR2_B200_SCHEME_LANGEVIN = 0, SEEKR2_B200_SCHEME_MIDDLE = 1 };
 
 /* boundary surface types: the typed form of the CustomCentroidBondForce expressions the
@@ -164,7 +164,11 @@ typedef struct seekr2_b200_buffers {
     void* d_pos_delta;            /* two-pass path only; may be NULL for the fused step            */
     const void* d_random;         /* float4 pool; NULL = in-kernel Philox (seekr2_b200_set_rng)    */
     int64_t random_anchor_stride; /* float4 elements between consecutive anchors' pools            */
-    void* d_old_velm;             /* VARIANT_REFERENCE two-pass path only: mixed4[A][Np] scratch   */
+    void* d_old_velm;             /* multi-pass scratch, mixed4[A][Np]: VARIANT_REFERENCE (start-of-step
+                                     velocity) and every MIDDLE MMVT engine (the velocity Part2 saves
+                                     before the O step, langevinMiddle.cu:41)                        */
+    void* d_old_delta;            /* MIDDLE multi-pass path only: mixed4[A][Np] (oldDelta,
+                                     CudaSeekr2Kernels.cpp:630-643)                                  */
 } seekr2_b200_buffers;
 
 /* one crossing event, as appended by the device to the per-anchor ring */
@@ -261,6 +265,12 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
 /* replaces integrate{Mmvt,Elber}LangevinPart1 (langevin.cu:7-59)                                  */
 int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index,
                      void* stream);
+/* MIDDLE scheme only: replaces integrate{Mmvt,Elber}LangevinMiddlePart2 (langevinMiddle.cu:28-61,
+   :125-157): half drift, O step, half drift -> posDelta / oldDelta; call between the velocity
+   constraints and the position constraints.  For the MIDDLE scheme seekr2_b200_kick is Part1 (force
+   kick, :7-21) and seekr2_b200_finish is decision + Part3 (:68-101) with the predicated bounce.       */
+int seekr2_b200_middle_drift(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index,
+                             void* stream);
 /* replaces Part2 + calcForcesAndEnergy(false,true,mask) + the host crossing block + mmvtBounce
    (CudaSeekr2Kernels.cpp:231-365 / :509-594): a one-block-per-anchor decision kernel followed by the
    streaming finish with the bounce predicated on the device-side decision.                         */

@@ -27,9 +27,14 @@ protected:
     explicit B200StepKernelBase(OpenMM::CudaContext& cu) : cu(cu) {}
     ~B200StepKernelBase();
     void create(const OpenMM::System& system, seekr2_b200_config& cfg, int seed);
+    std::string mmvtOutput, mmvtStats;
+    std::vector<int32_t> mmvtGroups;
     seekr2_b200_buffers buffers();
     void check(int status) const;                 /* non-zero status -> OpenMMException(last_error) */
     void stepTwoPass(double temperature, double friction, double stepSize, double tolerance);
+    void stepMiddle(double temperature, double friction, double stepSize, double tolerance);
+    void allocateScratch(bool oldVelm, bool oldDelta);
+    OpenMM::CudaArray oldVelm, oldDelta;          /* multi-pass scratch (CudaSeekr2Kernels.cpp:618-643) */
     void drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc);
     OpenMM::CudaContext& cu;
     seekr2_b200_handle handle = nullptr;
@@ -61,6 +66,17 @@ private:
     std::string outputFileName;
     std::vector<int32_t> labels;     /* source groups then destination groups */
     int numSrc = 0;
+};
+
+/* LangevinMiddle twins (Seekr2Kernels.h:115-172; CudaSeekr2Kernels.cpp:604-1177): same engine with
+ * scheme = SEEKR2_B200_SCHEME_MIDDLE and the three-pass call sequence kick / middle_drift / finish. */
+class B200IntegrateMmvtLangevinMiddleStepKernel : public IntegrateMmvtLangevinMiddleStepKernel, private B200StepKernelBase {
+public:
+    B200IntegrateMmvtLangevinMiddleStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu)
+        : IntegrateMmvtLangevinMiddleStepKernel(name, platform), B200StepKernelBase(cu) {}
+    void initialize(const OpenMM::System& system, const MmvtLangevinMiddleIntegrator& integrator) override;
+    void execute(OpenMM::ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) override;
+    double computeKineticEnergy(OpenMM::ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) override;
 };
 
 }  // namespace Seekr2Plugin

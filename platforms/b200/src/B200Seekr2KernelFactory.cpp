@@ -14,6 +14,7 @@ public:
         CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getPlatformData())->contexts[0];   /* :74 */
         if (name == IntegrateMmvtLangevinStepKernel::Name()) return new B200IntegrateMmvtLangevinStepKernel(name, platform, cu);
         if (name == IntegrateElberLangevinStepKernel::Name()) return new B200IntegrateElberLangevinStepKernel(name, platform, cu);
+        if (name == IntegrateMmvtLangevinMiddleStepKernel::Name()) return new B200IntegrateMmvtLangevinMiddleStepKernel(name, platform, cu);
         throw OpenMMException((std::string("Tried to create kernel with illegal kernel name '") + name + "'").c_str());  /* :83 */
     }
 };
@@ -27,6 +28,7 @@ extern "C" void registerKernelFactories() {
         auto* factory = new Seekr2Plugin::B200Seekr2KernelFactory();     /* never freed, like the reference (:52) */
         platform.registerKernelFactory(Seekr2Plugin::IntegrateMmvtLangevinStepKernel::Name(), factory);
         platform.registerKernelFactory(Seekr2Plugin::IntegrateElberLangevinStepKernel::Name(), factory);
+        platform.registerKernelFactory(Seekr2Plugin::IntegrateMmvtLangevinMiddleStepKernel::Name(), factory);
     } catch (std::exception&) {
         /* the CUDA platform is not available: ignore, like the reference (:58-60) */
     }

@@ -75,6 +75,33 @@ void B200StepKernelBase::stepTwoPass(double temperature, double friction, double
     integration.computeVirtualSites();                                                      /* :239 (groups with virtual sites are refused) */
 }
 
+void B200StepKernelBase::allocateScratch(bool needOldVelm, bool needOldDelta) {
+    const size_t elem = (cu.getUseDoublePrecision() || cu.getUseMixedPrecision()) ? 4 * sizeof(double) : 4 * sizeof(float);
+    if (needOldVelm && !oldVelm.isInitialized()) oldVelm.initialize(cu, cu.getPaddedNumAtoms(), elem, "b200OldVelm");
+    if (needOldDelta && !oldDelta.isInitialized()) oldDelta.initialize(cu, cu.getPaddedNumAtoms(), elem, "b200OldDelta");
+}
+
+/* CudaIntegrateMmvtLangevinMiddleStepKernel::execute, integration part (CudaSeekr2Kernels.cpp:756-802) */
+void B200StepKernelBase::stepMiddle(double temperature, double friction, double stepSize, double tolerance) {
+    CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
+    integration.setNextStepSize(stepSize);
+    if (temperature != prevTemp || friction != prevFriction || stepSize != prevStepSize) {   /* :734-748 */
+        check(seekr2_b200_set_params(handle, temperature, friction, stepSize));
+        prevTemp = temperature; prevFriction = friction; prevStepSize = stepSize;
+    }
+    seekr2_b200_buffers b = buffers();
+    b.d_old_velm = (void*) oldVelm.getDevicePointer();
+    b.d_old_delta = (void*) oldDelta.getDevicePointer();
+    void* stream = (void*) cu.getCurrentStream();
+    const int randomIndex = integration.prepareRandomNumbers(cu.getPaddedNumAtoms());       /* :762 */
+    check(seekr2_b200_kick(handle, &b, (uint32_t) randomIndex, stream));                    /* Part1 :763-767 */
+    integration.applyVelocityConstraints(tolerance);                                        /* :770 */
+    check(seekr2_b200_middle_drift(handle, &b, (uint32_t) randomIndex, stream));            /* Part2 :774-783 */
+    integration.applyConstraints(tolerance);                                                /* :787 */
+    check(seekr2_b200_finish(handle, &b, stream));                                          /* Part3 + CV + crossing + bounce :791-908 */
+    integration.computeVirtualSites();                                                      /* :799 */
+}
+
 void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc) {
     records.resize(4096);
     int64_t n = 0;
@@ -159,5 +186,50 @@ void B200IntegrateElberLangevinStepKernel::execute(ContextImpl& context, const E
 double B200IntegrateElberLangevinStepKernel::computeKineticEnergy(ContextImpl&, const ElberLangevinIntegrator& integrator) {
     return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :597-599 */
 }
+
+/* ---- MMVT, LangevinMiddle ---------------------------------------------------------------------------- */
+
+void B200IntegrateMmvtLangevinMiddleStepKernel::initialize(const System& system, const MmvtLangevinMiddleIntegrator& integrator) {
+    seekr2_b200_config cfg{};
+    cfg.kind = SEEKR2_B200_KIND_MMVT;
+    cfg.scheme = SEEKR2_B200_SCHEME_MIDDLE;
+    cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
+    const int32_t counter0 = integrator.getBounceCounter();
+    cfg.bounce_counter0 = &counter0;
+    create(system, cfg, integrator.getRandomNumberSeed());
+    allocateScratch(true, true);
+    mmvtOutput = integrator.getOutputFileName();
+    mmvtStats = integrator.getSaveStatisticsFileName();
+    if (!integrator.getSaveStateFileName().empty())
+        throw OpenMMException("B200 SEEKR2 plugin: saveStateFileName is not supported yet (SURVEY.md 8f rank 2)");
+    for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) mmvtGroups.push_back(integrator.getMilestoneGroup(i));
+    check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, mmvtOutput.c_str()));
+}
+
+void B200IntegrateMmvtLangevinMiddleStepKernel::execute(ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) {
+    cu.setAsCurrent();
+    if (cu.getStepCount() <= 0) {                                  /* :750-755 */
+        seekr2_b200_buffers b = buffers();
+        check(seekr2_b200_check_first_step(handle, &b, nullptr, (void*) cu.getCurrentStream()));
+    }
+    stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    drainTo(mmvtOutput, SEEKR2_B200_KIND_MMVT, mmvtGroups, 0);
+    if (!mmvtStats.empty() && !records.empty()) {
+        seekr2_b200_anchor_state st;
+        check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+        check(seekr2_b200_write_statistics(mmvtStats.c_str(), &st, mmvtGroups.data(), (int32_t) mmvtGroups.size()));
+    }
+    cu.setTime(cu.getTime() + integrator.getStepSize());           /* :911-914 */
+    cu.setStepCount(cu.getStepCount() + 1);
+    cu.reorderAtoms();
+}
+
+double B200IntegrateMmvtLangevinMiddleStepKernel::computeKineticEnergy(ContextImpl&, const MmvtLangevinMiddleIntegrator& integrator) {
+    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());
+}
+
+/* ElberLangevinMiddle: identical to B200IntegrateElberLangevinStepKernel with cfg.scheme = MIDDLE and
+   stepMiddle() in place of stepTwoPass() (CudaSeekr2Kernels.cpp:1032-1173); left to the maintainer who
+   can compile against OpenMM -- every C-ABI entry point it needs is exercised by tests/test_gpu_middle.py. */
 
 }  // namespace Seekr2Plugin

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseekr2_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -69,7 +69,7 @@ class Buffers(C.Structure):
     _fields_ = [
         ("d_posq", C.c_void_p), ("d_posq_correction", C.c_void_p), ("d_velm", C.c_void_p),
         ("d_force", C.c_void_p), ("d_pos_delta", C.c_void_p), ("d_random", C.c_void_p),
-        ("random_anchor_stride", C.c_int64), ("d_old_velm", C.c_void_p),
+        ("random_anchor_stride", C.c_int64), ("d_old_velm", C.c_void_p), ("d_old_delta", C.c_void_p),
     ]
 
 
@@ -107,6 +107,7 @@ SYMBOLS = {
     "seekr2_b200_step": (C.c_int, [_P, C.POINTER(Buffers), C.c_uint32, _P]),
     "seekr2_b200_kick": (C.c_int, [_P, C.POINTER(Buffers), C.c_uint32, _P]),
     "seekr2_b200_finish": (C.c_int, [_P, C.POINTER(Buffers), _P]),
+    "seekr2_b200_middle_drift": (C.c_int, [_P, C.POINTER(Buffers), C.c_uint32, _P]),
     "seekr2_b200_graph_begin": (C.c_int, [_P, _P]),
     "seekr2_b200_graph_end": (C.c_int, [_P, _P]),
     "seekr2_b200_graph_launch": (C.c_int, [_P, _P]),

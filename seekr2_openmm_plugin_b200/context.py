@@ -65,6 +65,7 @@ class Context:
         self.force = torch.zeros((A, 3, Np), dtype=torch.int64, device=dev)
         self.pos_delta = None          # allocated on first two-pass step
         self.old_velm = None
+        self.old_delta = None
         self.random = None             # allocated by the integrator (pool) or injected
         self.random_injected = False
         self.random_cursor = 0         # step slot inside the pool
@@ -100,14 +101,17 @@ class Context:
         b.d_random = self.random.data_ptr() if self.random is not None else None
         b.random_anchor_stride = int(self.random.shape[1]) if self.random is not None else 0
         b.d_old_velm = self.old_velm.data_ptr() if self.old_velm is not None else None
+        b.d_old_delta = self.old_delta.data_ptr() if self.old_delta is not None else None
         return b
 
     @property
     def stream_ptr(self) -> int:
         return self.stream.cuda_stream
 
-    def ensure_two_pass_buffers(self, need_old_velm: bool) -> None:
+    def ensure_two_pass_buffers(self, need_old_velm: bool, need_old_delta: bool = False) -> None:
         A, Np = self.num_anchors, self.padded_num_atoms
+        if need_old_delta and self.old_delta is None:
+            self.old_delta = torch.zeros((A, Np, 4), dtype=self.mixed_dtype, device=self.device)
         if self.pos_delta is None:
             self.pos_delta = torch.zeros((A, Np, 4), dtype=self.mixed_dtype, device=self.device)
         if need_old_velm and self.old_velm is None:

@@ -103,6 +103,7 @@ template <int P> Bufs<P> typed_bufs(const seekr2_b200_buffers* b) {
     t.random = (const float4*) b->d_random;
     t.random_anchor_stride = b->random_anchor_stride;
     t.old_velm = (typename Prec<P>::mixed4*) b->d_old_velm;
+    t.old_delta = (typename Prec<P>::mixed4*) b->d_old_delta;
     return t;
 }
 
@@ -169,14 +170,27 @@ template <int P> int launch_fused_kind(seekr2_b200_engine* h, const seekr2_b200_
 }
 
 template <int P> int launch_kick(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
-    kick_kernel<P><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), ri);
+    if (h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE)
+        middle_part1_kernel<P><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+    else
+        kick_kernel<P><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), ri);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
+template <int P> int launch_middle_drift(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
+    middle_part2_kernel<P><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), ri);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }
 
 template <int P, int KIND> int launch_finish(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
+    // the pending position (posq + corr + posDelta) is the same expression in both schemes
     decide_kernel<P, KIND, 0><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
-    finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+    if (h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE)
+        middle_finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+    else
+        finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }
@@ -446,18 +460,30 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
 
 int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index, void* stream) {
     if (int rc = check_bufs(h, bufs, true, true)) return rc;
-    if (h->cfg.scheme != SEEKR2_B200_SCHEME_LANGEVIN) return fail(SEEKR2_B200_ERR_INVALID, "the LangevinMiddle scheme has no multi-pass (constraint) path yet: use seekr2_b200_step");
-    if (h->cfg.variant == SEEKR2_B200_VARIANT_REFERENCE && h->cfg.kind == SEEKR2_B200_KIND_MMVT && !bufs->d_old_velm)
-        return fail(SEEKR2_B200_ERR_INVALID, "VARIANT_REFERENCE two-pass MMVT needs d_old_velm");
+    const bool middle = h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE;
+    if (h->cfg.kind == SEEKR2_B200_KIND_MMVT && (h->cfg.variant == SEEKR2_B200_VARIANT_REFERENCE || middle) && !bufs->d_old_velm)
+        return fail(SEEKR2_B200_ERR_INVALID, "multi-pass MMVT needs d_old_velm (VARIANT_REFERENCE and the MIDDLE scheme)");
+    if (middle && !bufs->d_old_delta) return fail(SEEKR2_B200_ERR_INVALID, "the MIDDLE multi-pass path needs d_old_delta");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
     return DISPATCH_PRECISION(h, launch_kick<SINGLE>(h, bufs, random_index, s), launch_kick<MIXED>(h, bufs, random_index, s),
                               launch_kick<DOUBLE>(h, bufs, random_index, s));
 }
 
+int seekr2_b200_middle_drift(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index, void* stream) {
+    if (int rc = check_bufs(h, bufs, true, true)) return rc;
+    if (h->cfg.scheme != SEEKR2_B200_SCHEME_MIDDLE) return fail(SEEKR2_B200_ERR_INVALID, "seekr2_b200_middle_drift is for the MIDDLE scheme only");
+    if (!bufs->d_old_delta) return fail(SEEKR2_B200_ERR_INVALID, "the MIDDLE multi-pass path needs d_old_delta");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    return DISPATCH_PRECISION(h, launch_middle_drift<SINGLE>(h, bufs, random_index, s), launch_middle_drift<MIXED>(h, bufs, random_index, s),
+                              launch_middle_drift<DOUBLE>(h, bufs, random_index, s));
+}
+
 int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream) {
     if (int rc = check_bufs(h, bufs, false, true)) return rc;
-    if (h->cfg.scheme != SEEKR2_B200_SCHEME_LANGEVIN) return fail(SEEKR2_B200_ERR_INVALID, "the LangevinMiddle scheme has no multi-pass (constraint) path yet: use seekr2_b200_step");
+    if (h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE && (!bufs->d_old_delta || (h->cfg.kind == SEEKR2_B200_KIND_MMVT && !bufs->d_old_velm)))
+        return fail(SEEKR2_B200_ERR_INVALID, "the MIDDLE multi-pass path needs d_old_delta (and d_old_velm for MMVT)");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
     h->slab_valid = false;   // the two-pass path does not maintain the slab

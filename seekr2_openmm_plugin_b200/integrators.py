@@ -217,6 +217,9 @@ class _B200LangevinBase:
             L.check(L.lib.seekr2_b200_step(self._handle, C.byref(bufs), random_index, ctx.stream_ptr))
         else:
             L.check(L.lib.seekr2_b200_kick(self._handle, C.byref(bufs), random_index, ctx.stream_ptr))
+            if self.SCHEME == L.SCHEME_MIDDLE:
+                # integration.applyVelocityConstraints(tol) (CudaSeekr2Kernels.cpp:770): none in the harness
+                L.check(L.lib.seekr2_b200_middle_drift(self._handle, C.byref(bufs), random_index, ctx.stream_ptr))
             # integration.applyConstraints(tol): the harness systems have no constraints
             L.check(L.lib.seekr2_b200_finish(self._handle, C.byref(bufs), ctx.stream_ptr))
             ctx.groups_dirty = True
@@ -227,7 +230,8 @@ class _B200LangevinBase:
         ctx = self.context
         self._update_params()
         if self.stepMode == "two_pass":
-            ctx.ensure_two_pass_buffers(self.variant == L.VARIANT_REFERENCE and self.KIND == L.KIND_MMVT)
+            middle = self.SCHEME == L.SCHEME_MIDDLE
+            ctx.ensure_two_pass_buffers(self.KIND == L.KIND_MMVT and (self.variant == L.VARIANT_REFERENCE or middle), middle)
         ctx.prepareForces()
         self._first_step_check()
         self._before_first_step()
@@ -407,7 +411,7 @@ class LangevinMiddleIntegrator(_B200LangevinBase):
 class MmvtLangevinMiddleIntegrator(MmvtLangevinIntegrator):
     """``Seekr2Plugin::MmvtLangevinMiddleIntegrator`` -- what the reference's examples instantiate
     (mmvt_demonstration3_tryp_benz_spherical.py:59).  Kernel: langevinMiddle.cu:7-101; a bounce negates
-    the velocity saved after the force kick (:41, :202-214).  Fused single-launch step only."""
+    the velocity saved after the force kick (:41, :202-214)."""
     SCHEME = L.SCHEME_MIDDLE
     KERNEL_NAME = "IntegrateMmvtLangevinMiddleStep"     # Seekr2Kernels.h:117-119
 

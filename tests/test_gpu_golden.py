@@ -28,8 +28,6 @@ def test_gpu_reproduces_golden(cuda_device, tmp_path, name, mode):
         steps_run = steps            # still run everything: the golden file covers the whole trajectory
     syn = make_syn()
     integ = make_integ(syn)
-    if mode == "two_pass" and integ.SCHEME == L.SCHEME_MIDDLE:
-        pytest.skip("the Middle scheme has no multi-pass path yet")
     path = str(tmp_path / "gpu.csv")
     integ.setOutputFileName(path)
     npad = (syn.system.getNumParticles() + 31) // 32 * 32

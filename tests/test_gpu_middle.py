@@ -139,11 +139,72 @@ def test_hostguest_and_elber_middle(cuda_device):
         assert H.stats_tuple(o.state(), 0) == H.stats_tuple(integ_e.getAnchorState(0), 0)
 
 
-def test_middle_has_no_multi_pass_path_yet(cuda_device):
-    syn = H.toy_system()
-    integ = H.make_mmvt_integrator(syn, "", middle=True)
+@pytest.mark.parametrize("precision", [L.SINGLE, L.MIXED, L.DOUBLE])
+def test_middle_multi_pass_stage_by_stage_vs_reference_kernels(cuda_device, precision):
+    """seekr2_b200_kick / middle_drift / finish == the reference's Part1 / Part2 / Part3 after every stage."""
+    import torch
+    ref = _ref_lib(precision)
+    n = 3000
+    pos, vel, masses = H.lattice_system(n, 41)
+    masses[::13] = 0.0
+    forces = H.gaussian_pool(43, n)[:, :3].astype(np.float64) * 300.0
+    hb = H.make_host_buffers(precision, pos, vel, masses, forces)
+    npad = hb.posq.shape[0]
+    pool = np.zeros((2 * npad, 4), dtype=np.float32)
+    pool[: npad + 64] = H.gaussian_pool(47, npad + 64)
+    ri = 29
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    integ = s2.MmvtLangevinMiddleIntegrator(300.0, 1.0, 0.002, "")
     integ.setStepMode("two_pass")
-    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
-    ctx.setPositions(syn.positions)
-    with pytest.raises(s2.Seekr2Error, match="multi-pass"):
-        integ.step(1)
+    ctx = s2.Context(system, integ, {"CudaPrecision": NAMES[precision]})
+    H.upload(ctx, [hb])
+    ctx.setRandomPool(pool)
+    integ._update_params()
+    ctx.ensure_two_pass_buffers(True, True)
+    vs, fs, ns = [C.c_double() for _ in range(3)], None, None
+    out = (C.c_double * 3)()
+    L.check(L.lib.seekr2_b200_get_params(integ._handle, out))
+    dev = cuda_device
+    t = lambda a: torch.from_numpy(a.copy()).to(dev)
+    posq, velm, force, rnd = t(hb.posq), t(hb.velm), t(hb.force), t(pool)
+    corr = t(hb.corr) if hb.corr is not None else None
+    delta, old_delta = torch.zeros((npad, 4), dtype=velm.dtype, device=dev), torch.zeros((npad, 4), dtype=velm.dtype, device=dev)
+    old_posq, old_velm = torch.zeros_like(posq), torch.zeros_like(velm)
+    params = torch.tensor([out[0], out[2]], dtype=velm.dtype, device=dev)
+    dt = torch.tensor([0.0, 0.002], dtype=velm.dtype, device=dev)
+    P = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
+    eq = lambda a, b, what: np.testing.assert_array_equal(a.cpu().numpy()[:n].view(np.uint8), b.cpu().numpy()[:n].view(np.uint8), err_msg=what)
+    bufs = ctx.buffers()
+    ref.ref_middle_part1(n, npad, P(velm), P(force), P(dt), 0, None)
+    L.check(L.lib.seekr2_b200_kick(integ._handle, C.byref(bufs), ri, ctx.stream_ptr))
+    ctx.stream.synchronize(); torch.cuda.synchronize()
+    eq(ctx.velm[0], velm, "velm after Part1")
+    ref.ref_middle_part2(n, P(velm), P(delta), P(old_delta), P(params), P(dt), P(old_velm), P(rnd), C.c_uint(ri), 0, None)
+    L.check(L.lib.seekr2_b200_middle_drift(integ._handle, C.byref(bufs), ri, ctx.stream_ptr))
+    ctx.stream.synchronize(); torch.cuda.synchronize()
+    eq(ctx.velm[0], velm, "velm after Part2"); eq(ctx.pos_delta[0], delta, "posDelta"); eq(ctx.old_delta[0], old_delta, "oldDelta")
+    eq(ctx.old_velm[0], old_velm, "oldVelm")
+    # emulate a constraint solver: perturb posDelta identically on both sides
+    bump = torch.zeros_like(delta); bump[:n:7, 0] = 1e-4
+    delta += bump; ctx.pos_delta[0] += bump
+    ref.ref_middle_part3(n, P(posq), P(velm), P(delta), P(old_delta), P(dt), P(old_posq), P(corr), 0, None)
+    L.check(L.lib.seekr2_b200_finish(integ._handle, C.byref(bufs), ctx.stream_ptr))
+    ctx.stream.synchronize(); torch.cuda.synchronize()
+    eq(ctx.velm[0], velm, "velm after Part3"); eq(ctx.posq[0], posq, "posq after Part3")
+    if corr is not None:
+        eq(ctx.posq_correction[0], corr, "posqCorrection after Part3")
+
+
+@pytest.mark.parametrize("variant", ["cuda", "reference"])
+def test_middle_multi_pass_trajectory_vs_oracle(cuda_device, variant):
+    syn = H.toy_system()
+    pool = H.gaussian_pool(H.SEED_BASE + 73, 8000 * 32)
+    rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, "", variant, middle=True), L.MIXED, 8000, pool)
+    integ = H.make_mmvt_integrator(syn, "", variant, middle=True)
+    grc, ctx, gb = S.run_gpu(syn, integ, L.MIXED, 8000, pool, mode="two_pass")
+    assert rc == grc == 0 and len(o.records()) > 3
+    assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0))
+    H.assert_state_equal(ob, gb, 1)
+    assert H.stats_tuple(o.state(), 2) == H.stats_tuple(integ.getAnchorState(0), 2)
