@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 3
+#define SEEKR2_B200_ABI_VERSION 4
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -98,22 +98,28 @@ enum { SEEKR2_B200_SCHEME_LANGEVIN = 0, SEEKR2_B200_SCHEME_MIDDLE = 1 };
 enum {
     SEEKR2_B200_CV_SPHERE_PAIR = 0,   /* u = distance(g_a,g_b)^2 - threshold^2   (demo3:37)        */
     SEEKR2_B200_CV_SPHERE_FIXED = 1,  /* u = |c(g_a) - center|^2 - threshold^2   (demo1:59)        */
-    SEEKR2_B200_CV_PLANE = 2          /* u = c(g_a)[axis] - threshold            (demo2:61)        */
+    SEEKR2_B200_CV_PLANE = 2,         /* u = c(g_a)[axis] - threshold            (demo2:61)        */
+    SEEKR2_B200_CV_PAIR_SUM = 3,      /* u = sum_{p < axis} distance(g_2p, g_2p+1)^2 - threshold^2, axis = number
+                                         of pairs, 1..3                            (demo4:27)        */
+    SEEKR2_B200_CV_ANGLE = 4          /* angle(g_0, g_1, g_2) - threshold, evaluated without acos as the
+                                         sign-equivalent  u = cos(threshold)*|a||b| - a.b  with a = c0 - c1,
+                                         b = c2 - c1 (u >= 0 <=> angle >= threshold)  (demo5:24)        */
 };
 enum { SEEKR2_B200_STYLE_STEP = 0, SEEKR2_B200_STYLE_RAW = 1 };
 
 typedef struct seekr2_b200_boundary {
     int32_t type;         /* SEEKR2_B200_CV_*                                                      */
     int32_t style;        /* SEEKR2_B200_STYLE_*                                                   */
-    int32_t group_a;      /* centroid group index                                                  */
-    int32_t group_b;      /* second centroid group (SPHERE_PAIR), else ignored                     */
-    int32_t axis;         /* 0,1,2 (PLANE), else ignored                                           */
+    int32_t groups[6];    /* centroid group indices: [0] (and [1] for SPHERE_PAIR); [0..2] for ANGLE;
+                             [0..2*axis-1] for PAIR_SUM                                             */
+    int32_t axis;         /* 0,1,2 (PLANE); number of pairs (PAIR_SUM); else ignored               */
     int32_t force_group;  /* OpenMM force group of the Force carrying the term.  MMVT sums group 1
                              only (hard-wired mask 2, CudaSeekr2Kernels.cpp:206,248)               */
     double bitcode;       /* STEP style multiplier (1,2,4,...)                                     */
     double k;             /* sign selects the side; magnitude matters only for RAW style          */
     double threshold;     /* radius (nm) or plane position (nm)                                    */
-    double center[3];     /* SPHERE_FIXED centre (nm)                                              */
+    double center[3];     /* SPHERE_FIXED centre (nm).  ANGLE: center[0] is overwritten by the library
+                             with cos(threshold)                                                    */
 } seekr2_b200_boundary;
 
 typedef struct seekr2_b200_config {

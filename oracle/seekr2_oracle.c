@@ -35,6 +35,8 @@
  *   SPHERE_PAIR  u = fma(dz,dz, fma(dy,dy, dx*dx)) - r*r,  d = C_a - C_b
  *   SPHERE_FIXED same with d = C_a - center
  *   PLANE        u = C_a[axis] - threshold
+ *   PAIR_SUM     u = (sum over pairs, left to right, of |C_2p - C_2p+1|^2) - r*r
+ *   ANGLE        u = cos(ref)*sqrt(|a|^2*|b|^2) - a.b,  a = C_0 - C_1, b = C_2 - C_1   (no acos: u >= 0 <=> angle >= ref)
  *   term = (k*u >= 0 ? bitcode : 0)   (STEP)   or   k*u   (RAW)
  *   value(force group) = sum of terms in boundary order, in double, starting from +0.0
  */
@@ -174,6 +176,8 @@ seekr2_oracle* seekr2_oracle_create(const seekr2_b200_config* cfg, int anchor) {
     if (cfg->num_boundaries > 0)
         memcpy(o->boundaries, cfg->boundaries + (size_t) anchor * cfg->num_boundaries,
                sizeof(seekr2_b200_boundary) * (size_t) cfg->num_boundaries);
+    for (int b = 0; b < cfg->num_boundaries; b++)
+        if (o->boundaries[b].type == SEEKR2_B200_CV_ANGLE) o->boundaries[b].center[0] = cos(o->boundaries[b].threshold);
     o->numMilestoneGroups = cfg->num_milestone_groups;
     o->numSrc = cfg->num_src; o->numDest = cfg->num_dest;
     for (int i = 0; i < cfg->num_src; i++) { o->srcGroups[i] = cfg->src_groups[i]; o->srcValues[i] = -INFINITY; }
@@ -255,15 +259,35 @@ void seekr2_oracle_centroids(const seekr2_oracle* o, const void* posq, const voi
     }
 }
 
+static double sqdist(const double* ca, const double* cb) {
+    double d0 = ca[0] - cb[0], d1 = ca[1] - cb[1], d2 = ca[2] - cb[2];
+    return fma(d2, d2, fma(d1, d1, d0 * d0));
+}
+
 static double boundary_term(const seekr2_b200_boundary* b, const double* cen) {
     double u;
-    const double* ca = cen + 3 * b->group_a;
+    const double* ca = cen + 3 * b->groups[0];
     if (b->type == SEEKR2_B200_CV_PLANE) {
         u = ca[b->axis] - b->threshold;
+    } else if (b->type == SEEKR2_B200_CV_PAIR_SUM) {
+        /* demo4:27: distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2, summed left to right */
+        double sum = sqdist(cen + 3 * b->groups[0], cen + 3 * b->groups[1]);
+        for (int p = 1; p < b->axis; p++) sum = sum + sqdist(cen + 3 * b->groups[2 * p], cen + 3 * b->groups[2 * p + 1]);
+        u = sum - b->threshold * b->threshold;
+    } else if (b->type == SEEKR2_B200_CV_ANGLE) {
+        /* demo5:24: angle(g1,g2,g3) - ref_angle, through its cosine (center[0] = cos(ref_angle)) */
+        const double* c1 = cen + 3 * b->groups[1];
+        const double* c2 = cen + 3 * b->groups[2];
+        double a[3], v[3];
+        for (int c = 0; c < 3; c++) { a[c] = ca[c] - c1[c]; v[c] = c2[c] - c1[c]; }
+        double dot = fma(a[2], v[2], fma(a[1], v[1], a[0] * v[0]));
+        double na2 = fma(a[2], a[2], fma(a[1], a[1], a[0] * a[0]));
+        double nb2 = fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]));
+        u = b->center[0] * sqrt(na2 * nb2) - dot;
     } else {
         double d[3];
         if (b->type == SEEKR2_B200_CV_SPHERE_PAIR) {
-            const double* cb = cen + 3 * b->group_b;
+            const double* cb = cen + 3 * b->groups[1];
             for (int c = 0; c < 3; c++) d[c] = ca[c] - cb[c];
         } else {
             for (int c = 0; c < 3; c++) d[c] = ca[c] - b->center[c];

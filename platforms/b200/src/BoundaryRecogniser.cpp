@@ -27,6 +27,12 @@ Typed recognise(std::string e, int numGroups) {
         t.type = SEEKR2_B200_CV_SPHERE_FIXED; t.cx = m[1]; t.cy = m[2]; t.cz = m[3]; t.thr = m[4]; return t; }
     if (numGroups == 1 && std::regex_match(u, m, std::regex(R"(([xyz])1-(\w+))"))) {
         t.type = SEEKR2_B200_CV_PLANE; t.axis = std::string("xyz").find(m[1].str()[0]); t.thr = m[2]; return t; }
+    if (numGroups == 4 && std::regex_match(u, m, std::regex(R"(distance\(g1,g2\)\^2\+distance\(g3,g4\)\^2-(\w+)\^2)"))) {
+        t.type = SEEKR2_B200_CV_PAIR_SUM; t.axis = 2; t.thr = m[1]; return t; }
+    if (numGroups == 6 && std::regex_match(u, m, std::regex(R"(distance\(g1,g2\)\^2\+distance\(g3,g4\)\^2\+distance\(g5,g6\)\^2-(\w+)\^2)"))) {
+        t.type = SEEKR2_B200_CV_PAIR_SUM; t.axis = 3; t.thr = m[1]; return t; }     /* demo4:27 */
+    if (numGroups == 3 && std::regex_match(u, m, std::regex(R"(angle\(g1,g2,g3\)-(\w+))"))) {
+        t.type = SEEKR2_B200_CV_ANGLE; t.thr = m[1]; return t; }                    /* demo5:24 */
     throw OpenMMException("B200 SEEKR2 plugin: cannot type boundary expression");
 }
 }  // namespace
@@ -58,8 +64,7 @@ B200BoundarySet recogniseBoundaries(const System& system) {
             force->getBondParameters(b, groups, params);
             seekr2_b200_boundary bd{};
             bd.type = t.type; bd.style = t.style; bd.axis = t.axis; bd.force_group = force->getForceGroup();
-            bd.group_a = base + groups[0];
-            bd.group_b = t.type == SEEKR2_B200_CV_SPHERE_PAIR ? base + groups[1] : 0;
+            for (size_t g = 0; g < groups.size() && g < 6; g++) bd.groups[g] = base + groups[g];
             bd.bitcode = value(params, "bitcode", 1.0);
             bd.k = t.kSign * value(params, "k", 1.0);
             bd.threshold = value(params, t.thr, 0.0);

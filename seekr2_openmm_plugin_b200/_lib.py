@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseekr2_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -26,7 +26,7 @@ VARIANT_CUDA, VARIANT_REFERENCE = 0, 1
 FLAG_RESTORE_CORRECTION = 1
 KIND_LANGEVIN, KIND_MMVT, KIND_ELBER = 0, 1, 2
 SCHEME_LANGEVIN, SCHEME_MIDDLE = 0, 1
-CV_SPHERE_PAIR, CV_SPHERE_FIXED, CV_PLANE = 0, 1, 2
+CV_SPHERE_PAIR, CV_SPHERE_FIXED, CV_PLANE, CV_PAIR_SUM, CV_ANGLE = 0, 1, 2, 3, 4
 STYLE_STEP, STYLE_RAW = 0, 1
 REC_MMVT, REC_ELBER_SRC, REC_ELBER_DEST, REC_ELBER_DEST_STAR = 0, 1, 2, 3
 
@@ -43,7 +43,7 @@ class Seekr2Error(RuntimeError):
 
 class Boundary(C.Structure):
     _fields_ = [
-        ("type", C.c_int32), ("style", C.c_int32), ("group_a", C.c_int32), ("group_b", C.c_int32),
+        ("type", C.c_int32), ("style", C.c_int32), ("groups", C.c_int32 * 6),
         ("axis", C.c_int32), ("force_group", C.c_int32),
         ("bitcode", C.c_double), ("k", C.c_double), ("threshold", C.c_double), ("center", C.c_double * 3),
     ]

@@ -7,6 +7,7 @@
 //   acc_g  = sum_i llrint((w_i * P_i) * 2^40)   int64 fixed point => independent of reduction order
 //   C_g    = (double) acc_g * 2^-40
 //   SPHERE_PAIR / SPHERE_FIXED: u = fma(dz,dz, fma(dy,dy, dx*dx)) - r*r ;  PLANE: u = C[axis] - thr
+//   PAIR_SUM: u = sum of squared pair distances - r*r ;  ANGLE: u = cos(ref)*sqrt(|a|^2 |b|^2) - a.b
 //   term = (k*u >= 0 ? bitcode : 0) (STEP) or k*u (RAW); value = in-order double sum of the terms
 #pragma once
 #include "arith.cuh"
@@ -108,21 +109,44 @@ __device__ __forceinline__ double cv_centroid(const CvShared& sh, int g, int c) 
     return __dmul_rn(__ll2double_rn(sh.acc[g * 3 + c]), kFixedInvScale);
 }
 
+__device__ __forceinline__ double cv_sqdist(const CvShared& sh, int ga, int gb) {
+    const double d0 = __dsub_rn(cv_centroid(sh, ga, 0), cv_centroid(sh, gb, 0));
+    const double d1 = __dsub_rn(cv_centroid(sh, ga, 1), cv_centroid(sh, gb, 1));
+    const double d2 = __dsub_rn(cv_centroid(sh, ga, 2), cv_centroid(sh, gb, 2));
+    return __fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0)));
+}
+
 // one boundary term; evaluated by lane b of warp 0 after the accumulators are complete
 __device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b) {
     double u;
     if (b.type == SEEKR2_B200_CV_PLANE) {
-        u = __dsub_rn(cv_centroid(sh, b.group_a, b.axis), b.threshold);
+        u = __dsub_rn(cv_centroid(sh, b.groups[0], b.axis), b.threshold);
+    } else if (b.type == SEEKR2_B200_CV_PAIR_SUM) {
+        double sum = cv_sqdist(sh, b.groups[0], b.groups[1]);
+        for (int p = 1; p < b.axis; p++) sum = __dadd_rn(sum, cv_sqdist(sh, b.groups[2 * p], b.groups[2 * p + 1]));
+        u = __dsub_rn(sum, __dmul_rn(b.threshold, b.threshold));
+    } else if (b.type == SEEKR2_B200_CV_ANGLE) {
+        double a[3], v[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double mid = cv_centroid(sh, b.groups[1], c);
+            a[c] = __dsub_rn(cv_centroid(sh, b.groups[0], c), mid);
+            v[c] = __dsub_rn(cv_centroid(sh, b.groups[2], c), mid);
+        }
+        const double dot = __fma_rn(a[2], v[2], __fma_rn(a[1], v[1], __dmul_rn(a[0], v[0])));
+        const double na2 = __fma_rn(a[2], a[2], __fma_rn(a[1], a[1], __dmul_rn(a[0], a[0])));
+        const double nb2 = __fma_rn(v[2], v[2], __fma_rn(v[1], v[1], __dmul_rn(v[0], v[0])));
+        u = __dsub_rn(__dmul_rn(b.center[0], __dsqrt_rn(__dmul_rn(na2, nb2))), dot);   // center[0] = cos(ref)
     } else {
         double dx, dy, dz;
         if (b.type == SEEKR2_B200_CV_SPHERE_PAIR) {
-            dx = __dsub_rn(cv_centroid(sh, b.group_a, 0), cv_centroid(sh, b.group_b, 0));
-            dy = __dsub_rn(cv_centroid(sh, b.group_a, 1), cv_centroid(sh, b.group_b, 1));
-            dz = __dsub_rn(cv_centroid(sh, b.group_a, 2), cv_centroid(sh, b.group_b, 2));
+            dx = __dsub_rn(cv_centroid(sh, b.groups[0], 0), cv_centroid(sh, b.groups[1], 0));
+            dy = __dsub_rn(cv_centroid(sh, b.groups[0], 1), cv_centroid(sh, b.groups[1], 1));
+            dz = __dsub_rn(cv_centroid(sh, b.groups[0], 2), cv_centroid(sh, b.groups[1], 2));
         } else {
-            dx = __dsub_rn(cv_centroid(sh, b.group_a, 0), b.center[0]);
-            dy = __dsub_rn(cv_centroid(sh, b.group_a, 1), b.center[1]);
-            dz = __dsub_rn(cv_centroid(sh, b.group_a, 2), b.center[2]);
+            dx = __dsub_rn(cv_centroid(sh, b.groups[0], 0), b.center[0]);
+            dy = __dsub_rn(cv_centroid(sh, b.groups[0], 1), b.center[1]);
+            dz = __dsub_rn(cv_centroid(sh, b.groups[0], 2), b.center[2]);
         }
         const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
         u = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));

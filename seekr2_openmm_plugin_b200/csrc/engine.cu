@@ -277,10 +277,12 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     for (int a = 0; a < cfg->num_anchors; a++)
         for (int i = 0; i < cfg->num_boundaries; i++) {
             const seekr2_b200_boundary& bd = cfg->boundaries[(size_t) a * cfg->num_boundaries + i];
-            if (bd.type < SEEKR2_B200_CV_SPHERE_PAIR || bd.type > SEEKR2_B200_CV_PLANE) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: unknown type %d", i, bd.type);
-            if (bd.group_a < 0 || bd.group_a >= cfg->num_groups) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group_a %d", i, bd.group_a);
-            if (bd.type == SEEKR2_B200_CV_SPHERE_PAIR && (bd.group_b < 0 || bd.group_b >= cfg->num_groups)) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group_b %d", i, bd.group_b);
+            if (bd.type < SEEKR2_B200_CV_SPHERE_PAIR || bd.type > SEEKR2_B200_CV_ANGLE) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: unknown type %d", i, bd.type);
             if (bd.type == SEEKR2_B200_CV_PLANE && (bd.axis < 0 || bd.axis > 2)) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad axis %d", i, bd.axis);
+            if (bd.type == SEEKR2_B200_CV_PAIR_SUM && (bd.axis < 1 || bd.axis > 3)) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: PAIR_SUM needs 1..3 pairs, got %d", i, bd.axis);
+            const int used = bd.type == SEEKR2_B200_CV_SPHERE_PAIR ? 2 : bd.type == SEEKR2_B200_CV_ANGLE ? 3 : bd.type == SEEKR2_B200_CV_PAIR_SUM ? 2 * bd.axis : 1;
+            for (int g = 0; g < used; g++)
+                if (bd.groups[g] < 0 || bd.groups[g] >= cfg->num_groups) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group index %d", i, bd.groups[g]);
         }
     if (cfg->kind == SEEKR2_B200_KIND_ELBER) {
         // every milestone's force group must carry a Force (CudaSeekr2Kernels.cpp:415-436)
@@ -339,8 +341,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     }
     if (cfg->num_boundaries > 0) {
         const size_t nb = (size_t) A * cfg->num_boundaries;
+        std::vector<Boundary> bounds(cfg->boundaries, cfg->boundaries + nb);
+        for (Boundary& bd : bounds)
+            if (bd.type == SEEKR2_B200_CV_ANGLE) bd.center[0] = cos(bd.threshold);   // compared through the cosine (no acos on the device)
         CREATE_TRY(cudaMalloc(&h->d_boundaries, sizeof(Boundary) * nb));
-        CREATE_TRY(cudaMemcpy(h->d_boundaries, cfg->boundaries, sizeof(Boundary) * nb, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_boundaries, bounds.data(), sizeof(Boundary) * nb, cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));

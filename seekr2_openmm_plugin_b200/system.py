@@ -128,6 +128,14 @@ def _recognise(expression: str, num_groups: int) -> _TypedExpression:
     m = re.fullmatch(r"([xyz])1-(\w+)", u)
     if num_groups == 1 and m:
         return _TypedExpression(L.CV_PLANE, style, axis="xyz".index(m.group(1)), k_sign=sign, threshold_name=m.group(2))
+    m = re.fullmatch(r"distance\(g1,g2\)\^2((?:\+distance\(g\d,g\d\)\^2)*)-(\w+)\^2", u)
+    if m and num_groups in (4, 6):
+        pairs = re.findall(r"distance\(g(\d),g(\d)\)", u)
+        if [int(x) for p in pairs for x in p] == list(range(1, num_groups + 1)):       # demo4:27
+            return _TypedExpression(L.CV_PAIR_SUM, style, axis=num_groups // 2, k_sign=sign, threshold_name=m.group(2))
+    m = re.fullmatch(r"angle\(g1,g2,g3\)-(\w+)", u)
+    if num_groups == 3 and m:                                                           # demo5:24
+        return _TypedExpression(L.CV_ANGLE, style, k_sign=sign, threshold_name=m.group(1))
     raise L.Seekr2Error(L.ERR_INVALID, f"cannot type boundary expression {expression!r}")
 
 
@@ -135,7 +143,8 @@ class CustomCentroidBondForce(Force):
     """The subset of OpenMM's ``CustomCentroidBondForce`` that SEEKR2 milestone definitions use.
 
     ``bitcode*step(k*(distance(g1,g2)^2-radius^2))`` (demo3:37), the fixed-centre sphere (demo1:59),
-    axis planes (demo2:61) and their older non-``step`` forms.  Per-bond parameters may be given per
+    axis planes (demo2:61), the sum of squared pair distances (demo4:27), the three-group angle
+    (demo5:24) and their older non-``step`` forms.  Per-bond parameters may be given per
     anchor (``setAnchorBondParameters``) so one engine can run many Voronoi cells of one system."""
 
     def __init__(self, numGroups: int, expression: str):
@@ -180,8 +189,8 @@ class CustomCentroidBondForce(Force):
             b = L.Boundary()
             b.type = t.cv_type
             b.style = t.style
-            b.group_a = group_base + groups[0]
-            b.group_b = group_base + groups[1] if t.cv_type == L.CV_SPHERE_PAIR else 0
+            for gi, g in enumerate(groups[:6]):
+                b.groups[gi] = group_base + g
             b.axis = t.axis
             b.force_group = self.getForceGroup()
             b.bitcode = p.get("bitcode", 1.0)

@@ -130,3 +130,57 @@ def test_full_size_properties(cuda_device, n_atoms, planes):
             H.assert_state_equal(H.download(ctx_l, 0), after, n_atoms, f"plain Langevin twin step {s}")
     assert bounced_steps >= 1, "the scenario must contain at least one bounce"
     assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0))
+
+
+def test_angle_and_pair_sum_boundaries_on_gpu(cuda_device):
+    """demo5-style angle milestones (two step-style bonds, inner and outer angle) and a demo4-style pair-sum
+    milestone on small solvated systems: trajectories, decisions and records bit-equal to the oracle."""
+    import math
+    n = 600
+    pos, vel, masses = H.lattice_system(n, H.SEED_BASE + 21)
+    pool = H.gaussian_pool(H.SEED_BASE + 22, 800 * 608)
+
+    def angle_system():
+        system = s2.System()
+        for m in masses:
+            system.addParticle(float(m))
+        f = s2.CustomCentroidBondForce(3, "bitcode*step(k*(angle(g1, g2, g3) - ref_angle))")
+        g = [f.addGroup([5, 6, 7]), f.addGroup([100, 101]), f.addGroup([300, 301, 302, 303])]
+        f.setForceGroup(1)
+        for name in ("bitcode", "k", "ref_angle"):
+            f.addPerBondParameter(name)
+        c = [np.average(pos[idx], axis=0, weights=masses[idx]) for idx in ([5, 6, 7], [100, 101], [300, 301, 302, 303])]
+        a, b = c[0] - c[1], c[2] - c[1]
+        ang = math.acos(a @ b / math.sqrt((a @ a) * (b @ b)))
+        f.addBond(g, [1.0, -1.0, ang - 0.004])
+        f.addBond(g, [2.0, 1.0, ang + 0.004])
+        system.addForce(f)
+        return system
+
+    def pair_sum_system():
+        system = s2.System()
+        for m in masses:
+            system.addParticle(float(m))
+        f = s2.CustomCentroidBondForce(6, "bitcode*step(k*(distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2))")
+        idx = [[1], [50], [2], [51], [3], [52]]
+        g = [f.addGroup(i) for i in idx]
+        f.setForceGroup(1)
+        for name in ("bitcode", "k", "radius"):
+            f.addPerBondParameter(name)
+        total = sum(((pos[idx[2 * p][0]] - pos[idx[2 * p + 1][0]]) ** 2).sum() for p in range(3))
+        f.addBond(g, [1.0, -1.0, math.sqrt(total) - 0.01])
+        f.addBond(g, [2.0, 1.0, math.sqrt(total) + 0.01])
+        system.addForce(f)
+        return system
+
+    for make in (angle_system, pair_sum_system):
+        system = make()
+        syn = H.Synthetic(system, pos, vel, masses, None, [1, 2], 0.0, 0.002)
+        rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, ""), L.MIXED, 800, pool)
+        integ = H.make_mmvt_integrator(syn, "")
+        grc, ctx, gb = S.run_gpu(syn, integ, L.MIXED, 800, pool, graph=16)
+        assert rc == grc == 0 and o.state().num_bounce_steps >= 2, make.__name__
+        _same(o, ob, integ, gb, n, 2)
+        integ2 = H.make_mmvt_integrator(syn, "")
+        grc, ctx, gb2 = S.run_gpu(syn, integ2, L.MIXED, 800, pool, mode="two_pass")
+        _same(o, ob, integ2, gb2, n, 2)

@@ -19,8 +19,14 @@ def test_recognises_reference_example_expressions():
     assert (f._typed.cv_type, f._typed.style, f._typed.axis, f._typed.k_sign) == (L.CV_PLANE, L.STYLE_RAW, 1, -1.0)
     f = s2.CustomCentroidBondForce(1, "bitcode*step(k*(z1-bound))")
     assert (f._typed.cv_type, f._typed.style, f._typed.axis) == (L.CV_PLANE, L.STYLE_STEP, 2)
+    f = s2.CustomCentroidBondForce(3, "-k*(angle(g1, g2, g3) - ref_angle)")                        # demo5:24
+    assert (f._typed.cv_type, f._typed.style, f._typed.k_sign, f._typed.threshold_name) == (L.CV_ANGLE, L.STYLE_RAW, -1.0, "ref_angle")
+    f = s2.CustomCentroidBondForce(6, "-k*(distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2)")   # demo4:27
+    assert (f._typed.cv_type, f._typed.axis, f._typed.k_sign) == (L.CV_PAIR_SUM, 3, -1.0)
     with pytest.raises(s2.Seekr2Error):
-        s2.CustomCentroidBondForce(3, "k*(angle(g1,g2,g3)-theta0)")                                # demo5: not typed yet
+        s2.CustomCentroidBondForce(2, "k*(distance(g1,g2)-radius)")                                # not a form the examples use
+    with pytest.raises(s2.Seekr2Error):
+        s2.CustomCentroidBondForce(4, "k*(dihedral(g1,g2,g3,g4)-phi0)")
 
 
 def test_lowering_matches_demo3_definition():
@@ -40,7 +46,7 @@ def test_lowering_matches_demo3_definition():
     assert list(low.group_offsets) == [0, 3, 5] and list(low.group_atoms) == [3, 5, 7, 10, 11]
     np.testing.assert_array_equal(low.group_weights, [4.0, 6.0, 8.0, 11.0, 12.0])      # masses: OpenMM's default weights
     b = low.boundaries[0][0]
-    assert (b.type, b.group_a, b.group_b, b.force_group, b.bitcode, b.k, b.threshold) == (L.CV_SPHERE_PAIR, 0, 1, 1, 1.0, -1.0, 1.1)
+    assert (b.type, b.groups[0], b.groups[1], b.force_group, b.bitcode, b.k, b.threshold) == (L.CV_SPHERE_PAIR, 0, 1, 1, 1.0, -1.0, 1.1)
     assert low.boundaries[0][1].threshold == 1.3 and low.boundaries[1][1].threshold == 1.5
 
 

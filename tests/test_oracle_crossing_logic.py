@@ -197,3 +197,53 @@ def test_log_files_append_and_restart(tmp_path):
     o.write_statistics(stats, syn.milestone_groups)
     lines = open(stats).read().splitlines()
     assert lines[0].startswith("N_alpha_1: ") and lines[-1].startswith("T_alpha: ") and len(lines) == 2 + 4 + 2 + 1
+
+
+def _three_particle_system(expr, ngroups, params, names, positions, style_groups=1):
+    system = s2.System()
+    for _ in range(len(positions)):
+        system.addParticle(12.0)
+    f = s2.CustomCentroidBondForce(ngroups, expr)
+    gs = [f.addGroup([i]) for i in range(ngroups)]
+    f.setForceGroup(1)
+    for n in names:
+        f.addPerBondParameter(n)
+    f.addBond(gs, params)
+    system.addForce(f)
+    integ = s2.MmvtLangevinIntegrator(0.0, 0.0, 0.01, "")
+    integ.addMilestoneGroup(1)
+    return system, integ
+
+
+def test_angle_boundary_matches_acos_definition():
+    """demo5:24 `angle(g1,g2,g3) - ref_angle`, evaluated through the cosine: same decisions as the acos form."""
+    import math
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        pos = rng.uniform(-1, 1, (3, 3))
+        ref = rng.uniform(0.2, 3.0)
+        a, b = pos[0] - pos[1], pos[2] - pos[1]
+        ang = math.acos(max(-1.0, min(1.0, float(a @ b / math.sqrt((a @ a) * (b @ b))))))
+        if abs(ang - ref) < 1e-6:
+            continue
+        for ksign in (1.0, -1.0):
+            system, integ = _three_particle_system("bitcode*step(k*(angle(g1,g2,g3)-ref_angle))", 3, [1.0, ksign, ref],
+                                                   ("bitcode", "k", "ref_angle"), pos)
+            o = H.oracle_for(integ, system, L.DOUBLE)
+            hb = H.make_host_buffers(L.DOUBLE, pos, np.zeros((3, 3)), np.full(3, 12.0))
+            expect = 1.0 if ksign * (ang - ref) >= 0 else 0.0
+            assert o.group_value(hb.posq, hb.corr, 1) == expect
+
+
+def test_pair_sum_boundary():
+    """demo4:27: distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2 (old non-step style)."""
+    pos = np.array([[0.0, 0, 0], [0.3, 0, 0], [1.0, 0, 0], [1.0, 0.4, 0], [2.0, 0, 0], [2.0, 0, 0.5]])
+    total = 0.09 + 0.16 + 0.25
+    for radius, ksign in ((0.6, -1.0), (0.8, -1.0), (0.6, 1.0), (0.8, 1.0)):
+        system, integ = _three_particle_system("-k*(distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2)" if ksign < 0
+                                               else "k*(distance(g1,g2)^2 + distance(g3,g4)^2 + distance(g5,g6)^2 - radius^2)",
+                                               6, [1.0e-9, radius], ("k", "radius"), pos)
+        o = H.oracle_for(integ, system, L.DOUBLE)
+        hb = H.make_host_buffers(L.DOUBLE, pos, np.zeros((6, 3)), np.full(6, 12.0))
+        value = o.group_value(hb.posq, hb.corr, 1)
+        assert abs(value - ksign * 1.0e-9 * (total - radius ** 2)) < 1e-20
