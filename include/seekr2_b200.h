@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 4
+#define SEEKR2_B200_ABI_VERSION 5
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -59,8 +59,10 @@ enum {
                                            (CudaSeekr2Kernels.cpp:205-210)                        */
     SEEKR2_B200_ERR_RING_OVERFLOW = 4,  /* crossing records were dropped: drain more often        */
     SEEKR2_B200_ERR_IO = 5,             /* crossing / statistics file could not be written        */
-    SEEKR2_B200_ERR_NO_FORCE_GROUP = 6  /* Elber: a milestone's force group has no boundary
+    SEEKR2_B200_ERR_NO_FORCE_GROUP = 6, /* Elber: a milestone's force group has no boundary
                                            (CudaSeekr2Kernels.cpp:415-436)                        */
+    SEEKR2_B200_ERR_SNAPSHOT_LOST = 7   /* a crossing-state snapshot was overwritten before it was
+                                           fetched: drain more often or raise save_state_slots     */
 };
 
 /* CudaPrecision of the owning context */
@@ -159,6 +161,10 @@ typedef struct seekr2_b200_config {
     const int32_t* crossing_counter0;   /* [num_anchors] or NULL                                   */
 
     int32_t ring_capacity;        /* crossing records kept per anchor between drains (0 = 4096)    */
+    int32_t save_state_slots;     /* > 0: keep the positions / velocities of the last `slots` single-
+                                     surface crossings per anchor as they were BEFORE the bounce
+                                     (saveStateFileName, CudaSeekr2Kernels.cpp:282-293, :575-587);
+                                     costs slots * 64 B per atom and anchor of device memory         */
 } seekr2_b200_config;
 
 /* device buffers of one step call (borrowed, never owned) */
@@ -190,7 +196,7 @@ typedef struct seekr2_b200_record {
     int32_t index;       /* bit index i (MMVT) or position in the src / dest list (Elber)          */
     int32_t counter;     /* bounceCounter / crossingCounter written on the line                    */
     int32_t num_surfaces;/* surfaces crossed in the same step (state is saved only when == 1)      */
-    int32_t reserved;
+    int32_t snapshot;    /* sequence number (1,2,...) of the saved crossing state, 0 = none          */
     int64_t step;        /* stepCount of the step that crossed                                     */
     double time;         /* context time written on the line (ps)                                  */
 } seekr2_b200_record;
@@ -216,6 +222,8 @@ typedef struct seekr2_b200_anchor_state {
     int32_t end_simulation;
     int32_t elber_sampled;       /* bit i set once milestone i has its baseline value              */
     float elber_values[SEEKR2_B200_MAX_ELBER]; /* src values then dest values                      */
+    int32_t num_snapshots;       /* crossing states saved so far (save_state_slots > 0)            */
+    int32_t reserved0;
 } seekr2_b200_anchor_state;
 
 typedef struct seekr2_b200_engine* seekr2_b200_handle;
@@ -302,6 +310,18 @@ int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anch
 /* Context::setTime / setStepCount analogue (used by reinitialize and by tests)                     */
 int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int64_t step_count,
                          void* stream);
+
+/* copy crossing-state snapshot `snapshot` (from a record) of `anchor` to the host as doubles:
+   positions[N][3] = posq (+ posqCorrection), velocities[N][3].  SEEKR2_B200_ERR_SNAPSHOT_LOST if more
+   than save_state_slots snapshots of that anchor were taken since.  Synchronises `stream`.          */
+int seekr2_b200_fetch_snapshot(seekr2_b200_handle h, int32_t anchor, int32_t snapshot, double* positions,
+                               double* velocities, void* stream);
+/* write positions / velocities as an OpenMM `State` XML document (version 1: PeriodicBoxVectors,
+   Positions, Velocities), the file the reference produces with XmlSerializer::serialize<State>
+   (CudaSeekr2Kernels.cpp:283-292).  box = 3x3 row vectors (nm) or NULL.  The exact number formatting of
+   OpenMM's serializer is not reproduced (OpenMM absent here); values are written with 17 digits.       */
+int seekr2_b200_write_state_xml(const char* path, int32_t num_atoms, const double* positions,
+                                const double* velocities, double time, const double* box);
 
 /* ---- crossing / statistics files (host side of CudaSeekr2Kernels.cpp:158-171,257-345,459-460) -- */
 

@@ -47,6 +47,8 @@ def load(structs):
     lib.seekr2_oracle_num_records.argtypes = [P]
     lib.seekr2_oracle_get_records.argtypes = [P, C.POINTER(structs.Record)]
     lib.seekr2_oracle_get_state.argtypes = [P, C.POINTER(structs.AnchorState)]
+    lib.seekr2_oracle_get_snapshot.restype = C.c_int
+    lib.seekr2_oracle_get_snapshot.argtypes = [P, C.c_int, P, P]
     lib.seekr2_oracle_set_time.argtypes = [P, C.c_double, C.c_int64]
     lib.seekr2_oracle_write_header.restype = C.c_int
     lib.seekr2_oracle_write_header.argtypes = [C.c_int, C.c_char_p]
@@ -108,6 +110,14 @@ class Oracle:
         st = self.S.AnchorState()
         self.lib.seekr2_oracle_get_state(self.h, C.byref(st))
         return st
+
+    def snapshot(self, seq):
+        """(positions[N,3], velocities[N,3]) of crossing state ``seq`` (Record.snapshot)."""
+        n = self.cfg.num_atoms
+        x, v = np.zeros((n, 3)), np.zeros((n, 3))
+        if self.lib.seekr2_oracle_get_snapshot(self.h, seq, ptr(x), ptr(v)) != 0:
+            raise IndexError(f"no crossing state {seq}")
+        return x, v
 
     def write_log(self, path, labels):
         arr = (C.c_int * max(1, len(labels)))(*labels)

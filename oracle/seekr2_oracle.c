@@ -133,6 +133,11 @@ typedef struct seekr2_oracle {
     /* crossing records */
     seekr2_b200_record* records;
     int64_t numRecords, capRecords;
+    /* crossing states (saveStateFileName, CudaSeekr2Kernels.cpp:282-293,575-587): every one is kept,
+       as doubles [numSnapshots][2][numAtoms][3] = what getState(Positions | Velocities) returns */
+    int saveStates;
+    double* snapshots;
+    int64_t capSnapshots;
 } seekr2_oracle;
 
 static size_t real4_size(int precision) { return precision == SEEKR2_B200_DOUBLE ? 32 : 16; }
@@ -142,7 +147,7 @@ void seekr2_oracle_destroy(seekr2_oracle* o) {
     if (!o) return;
     free(o->groupOffsets); free(o->groupAtoms); free(o->groupWeights); free(o->boundaries);
     free(o->posDelta); free(o->oldDelta); free(o->oldPosq); free(o->oldPosqCorrection); free(o->oldVelm);
-    free(o->startVelm); free(o->startForce); free(o->records);
+    free(o->startVelm); free(o->startForce); free(o->records); free(o->snapshots);
     free(o);
 }
 
@@ -183,6 +188,7 @@ seekr2_oracle* seekr2_oracle_create(const seekr2_b200_config* cfg, int anchor) {
     for (int i = 0; i < cfg->num_src; i++) { o->srcGroups[i] = cfg->src_groups[i]; o->srcValues[i] = -INFINITY; }
     for (int i = 0; i < cfg->num_dest; i++) { o->destGroups[i] = cfg->dest_groups[i]; o->destValues[i] = -INFINITY; }
     o->endOnSrcMilestone = cfg->end_on_src_milestone;
+    o->saveStates = cfg->save_state_slots > 0;
     /* initialize(): CudaSeekr2Kernels.cpp:118-133,151-154 and :403-404 */
     memset(&o->st, 0, sizeof(o->st));
     o->st.bounce_counter = cfg->bounce_counter0 ? cfg->bounce_counter0[anchor] : 0;
@@ -311,6 +317,46 @@ double seekr2_oracle_group_value(const seekr2_oracle* o, const void* posq, const
 
 /* ---- crossing records ---------------------------------------------------------------------- */
 
+/* `State myState = context.getOwner().getState(State::Positions | State::Velocities)` at the moment of
+   the crossing, i.e. after the position update and before the bounce (CudaSeekr2Kernels.cpp:283, :576):
+   positions = posq (+ posqCorrection in mixed precision), velocities = velm.  Returns the sequence
+   number (1, 2, ...) that the crossing's records carry. */
+static int take_snapshot(seekr2_oracle* o, const void* posq, const void* corr, const void* velm) {
+    const size_t per = 6 * (size_t) o->numAtoms;
+    if (o->st.num_snapshots == o->capSnapshots) {
+        o->capSnapshots = o->capSnapshots ? 2 * o->capSnapshots : 16;
+        o->snapshots = (double*) realloc(o->snapshots, sizeof(double) * per * (size_t) o->capSnapshots);
+    }
+    double* x = o->snapshots + per * (size_t) o->st.num_snapshots;
+    double* v = x + 3 * (size_t) o->numAtoms;
+    for (int i = 0; i < o->numAtoms; i++) {
+        if (o->precision == SEEKR2_B200_DOUBLE) {
+            const real4_d* q = (const real4_d*) posq; x[3 * i] = q[i].x; x[3 * i + 1] = q[i].y; x[3 * i + 2] = q[i].z;
+        } else {
+            const real4_s* q = (const real4_s*) posq; x[3 * i] = q[i].x; x[3 * i + 1] = q[i].y; x[3 * i + 2] = q[i].z;
+            if (o->precision == SEEKR2_B200_MIXED) {
+                const real4_s* c = (const real4_s*) corr;
+                x[3 * i] += (double) c[i].x; x[3 * i + 1] += (double) c[i].y; x[3 * i + 2] += (double) c[i].z;
+            }
+        }
+        if (o->precision == SEEKR2_B200_SINGLE) {
+            const mixed4_s* w = (const mixed4_s*) velm; v[3 * i] = w[i].x; v[3 * i + 1] = w[i].y; v[3 * i + 2] = w[i].z;
+        } else {
+            const mixed4_d* w = (const mixed4_d*) velm; v[3 * i] = w[i].x; v[3 * i + 1] = w[i].y; v[3 * i + 2] = w[i].z;
+        }
+    }
+    return ++o->st.num_snapshots;
+}
+/* positions[numAtoms][3], velocities[numAtoms][3] of crossing state `snapshot` (1-based); 0 on success */
+int seekr2_oracle_get_snapshot(const seekr2_oracle* o, int snapshot, double* positions, double* velocities) {
+    if (snapshot < 1 || snapshot > o->st.num_snapshots) return SEEKR2_B200_ERR_INVALID;
+    const size_t per = 6 * (size_t) o->numAtoms;
+    const double* x = o->snapshots + per * (size_t) (snapshot - 1);
+    if (positions) memcpy(positions, x, sizeof(double) * 3 * (size_t) o->numAtoms);
+    if (velocities) memcpy(velocities, x + 3 * (size_t) o->numAtoms, sizeof(double) * 3 * (size_t) o->numAtoms);
+    return SEEKR2_B200_OK;
+}
+
 static void push_record(seekr2_oracle* o, int kind, int index, int counter, int nsurf, double time) {
     if (o->numRecords == o->capRecords) {
         o->capRecords = o->capRecords ? 2 * o->capRecords : 1024;
@@ -418,6 +464,8 @@ int seekr2_oracle_mmvt_step(seekr2_oracle* o, void* posq, void* corr, void* velm
             if ((bitcode % 2) == 0) { bitcode = bitcode >> 1; continue; }
             bitcode = bitcode >> 1;
             push_record(o, SEEKR2_B200_REC_MMVT, i, o->st.bounce_counter, num_bounced_surfaces, o->st.time);  /* :281 */
+            if (o->saveStates && num_bounced_surfaces == 1)                    /* :282-293 */
+                o->records[o->numRecords - 1].snapshot = take_snapshot(o, posq, corr, velm);
             if (o->variant == SEEKR2_B200_VARIANT_REFERENCE || o->st.previous_milestone != -1)   /* :294-296 vs Reference :290 */
                 o->st.N_alpha_beta[i] += 1;
             if (o->st.previous_milestone != i) {                               /* :297-305 */
@@ -486,7 +534,8 @@ int seekr2_oracle_elber_step(seekr2_oracle* o, void* posq, void* corr, void* vel
             }
         }
         if (o->st.end_simulation) {                                            /* :573-589 */
-            for (int r = first_record; r < (int) o->numRecords; r++) o->records[r].num_surfaces = num_bounced_surfaces;
+            int seq = (o->saveStates && num_bounced_surfaces == 1) ? take_snapshot(o, posq, corr, velm) : 0;   /* :575-587 */
+            for (int r = first_record; r < (int) o->numRecords; r++) { o->records[r].num_surfaces = num_bounced_surfaces; o->records[r].snapshot = seq; }
             o->st.crossing_counter++;
         }
     }

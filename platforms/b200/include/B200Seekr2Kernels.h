@@ -28,6 +28,7 @@ protected:
     ~B200StepKernelBase();
     void create(const OpenMM::System& system, seekr2_b200_config& cfg, int seed);
     std::string mmvtOutput, mmvtStats;
+    std::string saveStateFileName;               /* empty = crossing states are not kept */
     std::vector<int32_t> mmvtGroups;
     seekr2_b200_buffers buffers();
     void check(int status) const;                 /* non-zero status -> OpenMMException(last_error) */

@@ -43,6 +43,8 @@ void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, i
     cfg.group_weights = boundarySet.groupWeights.data();
     cfg.num_boundaries = (int) boundarySet.boundaries.size();
     cfg.boundaries = boundarySet.boundaries.data();
+    /* the ring is drained in the step that crossed, so two slots are plenty */
+    cfg.save_state_slots = saveStateFileName.empty() ? 0 : 2;
     check(seekr2_b200_create(&cfg, &handle));
 }
 
@@ -108,6 +110,25 @@ void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::v
     check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
     if (n > 0) check(seekr2_b200_append_records(kind, file.c_str(), records.data(), n, 0, labels.data(), (int32_t) labels.size(), numSrc));
     records.resize((size_t) n);
+    /* saveStateFileName: the crossed configuration, kept on the device before the bounce, goes to
+       "<prefix>_<counter>_<milestone group>" (CudaSeekr2Kernels.cpp:282-293, Elber :575-587) */
+    int32_t written = 0;
+    for (const seekr2_b200_record& r : records) {
+        if (r.snapshot <= 0 || r.snapshot == written) continue;     /* Elber: one state per ending step */
+        written = r.snapshot;
+        const int n3 = 3 * cu.getNumAtoms();
+        std::vector<double> x(n3), v(n3), xo(n3), vo(n3);
+        check(seekr2_b200_fetch_snapshot(handle, 0, r.snapshot, x.data(), v.data(), (void*) cu.getCurrentStream()));
+        const std::vector<int>& order = cu.getAtomIndex();             /* undo OpenMM's atom reordering, as getState does */
+        for (int i = 0; i < cu.getNumAtoms(); i++)
+            for (int k = 0; k < 3; k++) { xo[3 * order[i] + k] = x[3 * i + k]; vo[3 * order[i] + k] = v[3 * i + k]; }
+        const int label = labels[(r.kind == SEEKR2_B200_REC_ELBER_DEST || r.kind == SEEKR2_B200_REC_ELBER_DEST_STAR) ? numSrc + r.index : r.index];
+        Vec3 a, b, c;
+        cu.getPeriodicBoxVectors(a, b, c);
+        const double box[9] = {a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2]};
+        const std::string name = saveStateFileName + "_" + std::to_string(r.counter) + "_" + std::to_string(label);
+        check(seekr2_b200_write_state_xml(name.c_str(), cu.getNumAtoms(), xo.data(), vo.data(), r.time, box));
+    }
 }
 
 /* ---- MMVT ------------------------------------------------------------------------------------------- */
@@ -118,11 +139,10 @@ void B200IntegrateMmvtLangevinStepKernel::initialize(const System& system, const
     cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
     const int32_t counter0 = integrator.getBounceCounter();        /* :151 */
     cfg.bounce_counter0 = &counter0;
+    saveStateFileName = integrator.getSaveStateFileName();          /* :135-139 */
     create(system, cfg, integrator.getRandomNumberSeed());
     outputFileName = integrator.getOutputFileName();
     saveStatisticsFileName = integrator.getSaveStatisticsFileName();
-    if (!integrator.getSaveStateFileName().empty())
-        throw OpenMMException("B200 SEEKR2 plugin: saveStateFileName is not supported yet (SURVEY.md 8f rank 2)");
     for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) milestoneGroups.push_back(integrator.getMilestoneGroup(i));
     check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, outputFileName.c_str()));          /* :158-171 */
 }
@@ -162,6 +182,7 @@ void B200IntegrateElberLangevinStepKernel::initialize(const System& system, cons
     cfg.end_on_src_milestone = integrator.getEndOnSrcMilestone();  /* :414 */
     const int32_t counter0 = integrator.getCrossingCounter();      /* :403 */
     cfg.crossing_counter0 = &counter0;
+    saveStateFileName = integrator.getSaveStateFileName();          /* :405-409 */
     create(system, cfg, integrator.getRandomNumberSeed());          /* missing force group -> the reference's message (:421-422) */
     outputFileName = integrator.getOutputFileName();
     labels = src; labels.insert(labels.end(), dest.begin(), dest.end());
@@ -196,12 +217,11 @@ void B200IntegrateMmvtLangevinMiddleStepKernel::initialize(const System& system,
     cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
     const int32_t counter0 = integrator.getBounceCounter();
     cfg.bounce_counter0 = &counter0;
+    saveStateFileName = integrator.getSaveStateFileName();
     create(system, cfg, integrator.getRandomNumberSeed());
     allocateScratch(true, true);
     mmvtOutput = integrator.getOutputFileName();
     mmvtStats = integrator.getSaveStatisticsFileName();
-    if (!integrator.getSaveStateFileName().empty())
-        throw OpenMMException("B200 SEEKR2 plugin: saveStateFileName is not supported yet (SURVEY.md 8f rank 2)");
     for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) mmvtGroups.push_back(integrator.getMilestoneGroup(i));
     check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, mmvtOutput.c_str()));
 }

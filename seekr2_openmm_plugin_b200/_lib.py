@@ -14,13 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseekr2_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
 MAX_ELBER = 16
 
-OK, ERR_INVALID, ERR_CUDA, ERR_FIRST_STEP, ERR_RING_OVERFLOW, ERR_IO, ERR_NO_FORCE_GROUP = range(7)
+OK, ERR_INVALID, ERR_CUDA, ERR_FIRST_STEP, ERR_RING_OVERFLOW, ERR_IO, ERR_NO_FORCE_GROUP, ERR_SNAPSHOT_LOST = range(8)
 SINGLE, MIXED, DOUBLE = 0, 1, 2
 VARIANT_CUDA, VARIANT_REFERENCE = 0, 1
 FLAG_RESTORE_CORRECTION = 1
@@ -61,7 +61,7 @@ class Config(C.Structure):
         ("num_src", C.c_int32), ("src_groups", C.POINTER(C.c_int32)),
         ("num_dest", C.c_int32), ("dest_groups", C.POINTER(C.c_int32)),
         ("end_on_src_milestone", C.c_int32), ("crossing_counter0", C.POINTER(C.c_int32)),
-        ("ring_capacity", C.c_int32),
+        ("ring_capacity", C.c_int32), ("save_state_slots", C.c_int32),
     ]
 
 
@@ -76,7 +76,7 @@ class Buffers(C.Structure):
 class Record(C.Structure):
     _fields_ = [
         ("anchor", C.c_int32), ("kind", C.c_int32), ("index", C.c_int32), ("counter", C.c_int32),
-        ("num_surfaces", C.c_int32), ("reserved", C.c_int32), ("step", C.c_int64), ("time", C.c_double),
+        ("num_surfaces", C.c_int32), ("snapshot", C.c_int32), ("step", C.c_int64), ("time", C.c_double),
     ]
 
 
@@ -90,6 +90,7 @@ class AnchorState(C.Structure):
         ("last_value_positive", C.c_int32),
         ("crossing_counter", C.c_int32), ("crossed_src", C.c_int32), ("end_simulation", C.c_int32),
         ("elber_sampled", C.c_int32), ("elber_values", C.c_float * MAX_ELBER),
+        ("num_snapshots", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -114,6 +115,8 @@ SYMBOLS = {
     "seekr2_b200_drain": (C.c_int, [_P, C.POINTER(Record), C.c_int64, C.POINTER(C.c_int64), _P]),
     "seekr2_b200_get_state": (C.c_int, [_P, C.c_int32, C.POINTER(AnchorState), _P]),
     "seekr2_b200_set_time": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int64, _P]),
+    "seekr2_b200_fetch_snapshot": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
+    "seekr2_b200_write_state_xml": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]),
     "seekr2_b200_write_header": (C.c_int, [C.c_int32, C.c_char_p]),
     "seekr2_b200_append_records": (C.c_int, [C.c_int32, C.c_char_p, C.POINTER(Record), C.c_int64, C.c_int32,
                                              C.POINTER(C.c_int32), C.c_int32, C.c_int32]),

@@ -47,7 +47,12 @@ struct EngineDev {
     int* head_start;             // [2] decide blocks that have issued their gathers (per launch parity)
     int first_wave_blocks;       // streaming blocks resident at kernel start (they wait for head_start)
     int head_start_target;       // A x warps per decide block that hold group slots
-    int* flags;                  // [2][A] decision hand-off of the fused kernel (0 = not yet, 1 = advance, 3 = bounce)
+    int* flags;                  // [2][A] decision hand-off of the fused kernel: 0 = not yet; bit0 valid, bit1 bounce,
+                                 // bit2 save the advanced state into snapshot slot (flag >> 4)
+    int snap_slots;              // save_state_slots (0 = off)
+    void* snap_posq;             // real4 [A][slots][Np]   pre-bounce positions of the last crossings
+    void* snap_corr;             // real4 [A][slots][Np]   (MIXED only)
+    void* snap_velm;             // mixed4[A][slots][Np]
 };
 
 // shared-memory scratch of the CV phase
@@ -179,18 +184,36 @@ __device__ __forceinline__ double cv_group_value(const CvShared& sh, int num_bou
     return value;
 }
 
+constexpr int kFlagValid = 1, kFlagBounce = 2, kFlagSnapshot = 4, kFlagSlotShift = 4;
+
+// If crossing states are kept and exactly one surface is crossed, claims the next snapshot slot:
+// returns the flag bits for the streaming blocks and the snapshot's sequence number (0 = none).
+__device__ __forceinline__ int claim_snapshot(const EngineDev& e, AnchorState& st, int num_surfaces, int& seq) {
+    seq = 0;
+    if (e.snap_slots <= 0 || num_surfaces != 1) return 0;
+    seq = ++st.num_snapshots;
+    return kFlagSnapshot | (((seq - 1) % e.snap_slots) << kFlagSlotShift);
+}
+
+// number of logged surfaces in an MMVT value (CudaSeekr2Kernels.cpp:264-270)
+__device__ __forceinline__ int mmvt_num_surfaces(const EngineDev& e, float value) {
+    int bitcode = (int) value, n = 0;
+    for (int i = 0; i < e.num_milestone_groups; i++) { if ((bitcode % 2) != 0) n++; bitcode = bitcode >> 1; }
+    return n;
+}
+
 __device__ __forceinline__ void ring_append(const EngineDev& e, AnchorState& st, int anchor, int kind,
-                                            int index, int counter, int nsurf, double time) {
+                                            int index, int counter, int nsurf, double time, int snapshot = 0) {
     Record r;
     r.anchor = anchor; r.kind = kind; r.index = index; r.counter = counter;
-    r.num_surfaces = nsurf; r.reserved = 0; r.step = st.step_count; r.time = time;
+    r.num_surfaces = nsurf; r.snapshot = snapshot; r.step = st.step_count; r.time = time;
     e.ring[(size_t) anchor * e.ring_capacity + (size_t) (st.ring_head % e.ring_capacity)] = r;
     st.ring_head++;
 }
 
 // The host block of CudaIntegrateMmvtLangevinStepKernel::execute (CudaSeekr2Kernels.cpp:250-347),
 // run by one thread of the anchor's first block.  Returns whether the step bounces.
-__device__ __forceinline__ bool mmvt_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, float value) {
+__device__ __forceinline__ bool mmvt_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, float value, int snapshot = 0) {
     st.last_value_positive = value > 0.0f;
     if (!(value > 0.0f)) return false;
     int bitcode = (int) value;                                     // :262
@@ -203,7 +226,7 @@ __device__ __forceinline__ bool mmvt_bookkeeping(const EngineDev& e, AnchorState
     for (int i = 0; i < e.num_milestone_groups; i++) {              // :273-310
         if ((bitcode % 2) == 0) { bitcode = bitcode >> 1; continue; }
         bitcode = bitcode >> 1;
-        ring_append(e, st, anchor, SEEKR2_B200_REC_MMVT, i, st.bounce_counter, num_bounced_surfaces, st.time);
+        ring_append(e, st, anchor, SEEKR2_B200_REC_MMVT, i, st.bounce_counter, num_bounced_surfaces, st.time, snapshot);
         if (e.variant == SEEKR2_B200_VARIANT_REFERENCE || st.previous_milestone != -1)   // :294-296 / Reference :290
             st.N_alpha_beta[i] += 1;
         if (st.previous_milestone != i) {                           // :297-305
@@ -226,8 +249,9 @@ __device__ __forceinline__ bool mmvt_bookkeeping(const EngineDev& e, AnchorState
 // The crossing block of CudaIntegrateElberLangevinStepKernel::execute (CudaSeekr2Kernels.cpp:517-590).
 // elber_values holds the stored source values then destination values; elber_sampled marks which
 // have their baseline (the reference uses -INFINITY as "unsampled").
-__device__ __forceinline__ void elber_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, const CvShared& sh) {
-    if (st.end_simulation) return;                                  // :524
+// Returns the snapshot flag bits (0 = none) when the run just ended on exactly one surface (:575).
+__device__ __forceinline__ int elber_bookkeeping(const EngineDev& e, AnchorState& st, int anchor, const CvShared& sh) {
+    if (st.end_simulation) return 0;                                  // :524
     const long long head0 = st.ring_head;
     int num_bounced_surfaces = 0;
     for (int i = 0; i < e.num_src; i++) {                           // :526-549
@@ -261,11 +285,18 @@ __device__ __forceinline__ void elber_bookkeeping(const EngineDev& e, AnchorStat
                         st.crossing_counter, 0, st.time);
         }
     }
+    int snap_bits = 0;
     if (st.end_simulation) {                                        // :573-589
-        for (long long h = head0; h < st.ring_head; h++)
-            e.ring[(size_t) anchor * e.ring_capacity + (size_t) (h % e.ring_capacity)].num_surfaces = num_bounced_surfaces;
+        int seq = 0;
+        snap_bits = claim_snapshot(e, st, num_bounced_surfaces, seq);
+        for (long long h = head0; h < st.ring_head; h++) {
+            Record& r = e.ring[(size_t) anchor * e.ring_capacity + (size_t) (h % e.ring_capacity)];
+            r.num_surfaces = num_bounced_surfaces;
+            r.snapshot = seq;
+        }
         st.crossing_counter++;
     }
+    return snap_bits;
 }
 
 // step epilogue: CudaSeekr2Kernels.cpp:362-364 (MMVT) / :592-593 (Elber)

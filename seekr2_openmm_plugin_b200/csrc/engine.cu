@@ -79,6 +79,9 @@ struct seekr2_b200_engine {
     int* d_decision = nullptr;
     int* d_flags = nullptr;
     long long* d_step_shadow = nullptr;
+    void* d_snap_posq = nullptr;
+    void* d_snap_corr = nullptr;
+    void* d_snap_velm = nullptr;
     // host mirrors for drain
     AnchorState* h_state = nullptr;           // pinned [A]
     std::vector<long long> ring_tail;         // records already drained, per anchor
@@ -227,6 +230,7 @@ int seekr2_b200_destroy(seekr2_b200_handle h) {
     cudaFree(h->d_slot_atom); cudaFree(h->d_slot_group); cudaFree(h->d_slot_weight);
     cudaFree(h->d_boundaries); cudaFree(h->d_state); cudaFree(h->d_ring); cudaFree(h->d_slab);
     cudaFree(h->d_decision); cudaFree(h->d_flags); cudaFree(h->d_step_shadow);
+    cudaFree(h->d_snap_posq); cudaFree(h->d_snap_corr); cudaFree(h->d_snap_velm);
     if (h->h_state) cudaFreeHost(h->h_state);
     delete h;
     return SEEKR2_B200_OK;
@@ -370,6 +374,16 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
     d.decision = h->d_decision; d.flags = h->d_flags; d.step_shadow = h->d_step_shadow;
     d.rng_seed = 0; d.rng_anchor_base = 0; d.probe = nullptr;
+    d.snap_slots = cfg->save_state_slots > 0 ? cfg->save_state_slots : 0;
+    if (d.snap_slots > 0) {
+        if (d.snap_slots >= (1 << 20)) return bail(fail(SEEKR2_B200_ERR_INVALID, "too many save_state_slots"));
+        const size_t per = (size_t) A * d.snap_slots * cfg->padded_num_atoms;
+        const size_t real4_b = cfg->precision == DOUBLE ? 32 : 16, mixed4_b = cfg->precision == SINGLE ? 16 : 32;
+        CREATE_TRY(cudaMalloc(&h->d_snap_posq, per * real4_b));
+        CREATE_TRY(cudaMalloc(&h->d_snap_velm, per * mixed4_b));
+        if (cfg->precision == MIXED) CREATE_TRY(cudaMalloc(&h->d_snap_corr, per * real4_b));
+    }
+    d.snap_posq = h->d_snap_posq; d.snap_corr = h->d_snap_corr; d.snap_velm = h->d_snap_velm;
     d.head_start = h->d_flags + 2 * A;
     {
         cudaDeviceProp prop;
@@ -583,6 +597,62 @@ int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int6
     CUDA_TRY(cudaMemcpy(&h->d_state[anchor].step_count, &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
     for (int par = 0; par < 2; par++)
         CUDA_TRY(cudaMemcpy(&h->d_step_shadow[par * h->cfg.num_anchors + anchor], &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_fetch_snapshot(seekr2_b200_handle h, int32_t anchor, int32_t snapshot, double* positions, double* velocities, void* stream) {
+    if (!h || anchor < 0 || anchor >= h->cfg.num_anchors || snapshot < 1 || (!positions && !velocities)) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    if (h->dev.snap_slots <= 0) return fail(SEEKR2_B200_ERR_INVALID, "the engine was created with save_state_slots = 0");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    AnchorState st;
+    CUDA_TRY(cudaMemcpyAsync(&st, h->d_state + anchor, sizeof(AnchorState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (snapshot > st.num_snapshots) return fail(SEEKR2_B200_ERR_INVALID, "snapshot %d has not been taken yet", snapshot);
+    if (st.num_snapshots - snapshot >= h->dev.snap_slots)
+        return fail(SEEKR2_B200_ERR_SNAPSHOT_LOST, "crossing state %d of anchor %d was overwritten (%d taken since, %d slots)", snapshot, anchor, st.num_snapshots - snapshot, h->dev.snap_slots);
+    const int N = h->cfg.num_atoms, Np = h->cfg.padded_num_atoms;
+    const size_t off = ((size_t) anchor * h->dev.snap_slots + (snapshot - 1) % h->dev.snap_slots) * Np;
+    const size_t real_b = h->cfg.precision == DOUBLE ? 8 : 4, mixed_b = h->cfg.precision == SINGLE ? 4 : 8;
+    std::vector<char> x(N * 4 * real_b), c(h->cfg.precision == MIXED ? N * 4 * real_b : 0), v(N * 4 * mixed_b);
+    CUDA_TRY(cudaMemcpyAsync(x.data(), (char*) h->d_snap_posq + off * 4 * real_b, x.size(), cudaMemcpyDeviceToHost, s));
+    if (!c.empty()) CUDA_TRY(cudaMemcpyAsync(c.data(), (char*) h->d_snap_corr + off * 4 * real_b, c.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(v.data(), (char*) h->d_snap_velm + off * 4 * mixed_b, v.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < 3; k++) {
+            if (positions) {
+                double p = real_b == 8 ? ((double*) x.data())[4 * i + k] : (double) ((float*) x.data())[4 * i + k];
+                if (!c.empty()) p += (double) ((float*) c.data())[4 * i + k];     // what getState(Positions) returns in mixed precision
+                positions[3 * i + k] = p;
+            }
+            if (velocities) velocities[3 * i + k] = mixed_b == 8 ? ((double*) v.data())[4 * i + k] : (double) ((float*) v.data())[4 * i + k];
+        }
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_write_state_xml(const char* path, int32_t num_atoms, const double* positions, const double* velocities, double time, const double* box) {
+    if (!path || num_atoms < 0 || (!positions && !velocities)) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    FILE* f = fopen(path, "w");                       // std::ios_base::trunc (:290)
+    if (!f) return fail(SEEKR2_B200_ERR_IO, "cannot open %s", path);
+    fprintf(f, "<?xml version=\"1.0\" ?>\n<State time=\"%.17g\" type=\"State\" version=\"1\">\n", time);
+    static const double zero_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const double* bx = box ? box : zero_box;
+    fprintf(f, "\t<PeriodicBoxVectors>\n");
+    for (int r = 0; r < 3; r++) fprintf(f, "\t\t<%c x=\"%.17g\" y=\"%.17g\" z=\"%.17g\"/>\n", "ABC"[r], bx[3 * r], bx[3 * r + 1], bx[3 * r + 2]);
+    fprintf(f, "\t</PeriodicBoxVectors>\n");
+    if (positions) {
+        fprintf(f, "\t<Positions>\n");
+        for (int i = 0; i < num_atoms; i++) fprintf(f, "\t\t<Position x=\"%.17g\" y=\"%.17g\" z=\"%.17g\"/>\n", positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+        fprintf(f, "\t</Positions>\n");
+    }
+    if (velocities) {
+        fprintf(f, "\t<Velocities>\n");
+        for (int i = 0; i < num_atoms; i++) fprintf(f, "\t\t<Velocity x=\"%.17g\" y=\"%.17g\" z=\"%.17g\"/>\n", velocities[3 * i], velocities[3 * i + 1], velocities[3 * i + 2]);
+        fprintf(f, "\t</Velocities>\n");
+    }
+    fprintf(f, "</State>\n");
+    fclose(f);
     return SEEKR2_B200_OK;
 }
 

@@ -49,6 +49,7 @@ class _B200LangevinBase:
         self.useGraph = False
         self.stepsPerGraph = 32
         self.ringCapacity = 0
+        self.saveStateSlots = 32       # crossing states kept on the device between drains (saveStateFileName set)
         self.useRandomPool = False     # True: Gaussian pool refilled by a harness kernel (OpenMM style)
         self.rngAnchorBase = 0         # global index of the context's first anchor (multi-GPU runs)
         self._steps_issued = 0
@@ -125,6 +126,7 @@ class _B200LangevinBase:
                 flat[a * nb + i] = b
         cfg.boundaries = flat
         cfg.ring_capacity = self.ringCapacity
+        cfg.save_state_slots = self.saveStateSlots if (self.saveStateFileName and self.KIND != L.KIND_LANGEVIN) else 0
         self._keep_refs = [offs, atoms, wts, flat]
         self._fill_config(cfg, num_anchors)
         return cfg
@@ -228,6 +230,12 @@ class _B200LangevinBase:
         if self.context is None:
             raise L.Seekr2Error(L.ERR_INVALID, "This Integrator is not bound to a context!")
         ctx = self.context
+        if self.saveStateFileName and self.KIND != L.KIND_LANGEVIN and steps > self.saveStateSlots:
+            # a step saves at most one crossing state per anchor, so draining every `slots` steps can
+            # never lose one (the reference writes the file inside the step, CudaSeekr2Kernels.cpp:282-293)
+            for first in range(0, steps, self.saveStateSlots):
+                self.step(min(self.saveStateSlots, steps - first))
+            return
         self._update_params()
         if self.stepMode == "two_pass":
             middle = self.SCHEME == L.SCHEME_MIDDLE
@@ -308,9 +316,51 @@ class _B200LangevinBase:
             if n.value < self._DRAIN_CHUNK:
                 break
         self._records.extend(new)
+        self._save_states(new)
         if status != L.OK:
             raise L.Seekr2Error(status, "crossing ring overflowed: records were lost; drain more often or raise ringCapacity")
         return new
+
+    def stateFileName(self, record: L.Record) -> str:
+        """``saveStateFileName + "_" + counter + "_" + milestoneGroup`` (CudaSeekr2Kernels.cpp:285-287, :578-580)."""
+        labels = self._labels(record.anchor)
+        idx = record.index + (self._num_src() if record.kind in (L.REC_ELBER_DEST, L.REC_ELBER_DEST_STAR) else 0)
+        prefix = self.saveStateFileName
+        if self.context is not None and self.context.num_anchors > 1:
+            prefix = f"{prefix}.{record.anchor}"
+        return f"{prefix}_{record.counter}_{labels[idx]}"
+
+    def fetchCrossingState(self, record: L.Record):
+        """(positions[N,3], velocities[N,3]) as they were when ``record``'s surface was crossed, before
+        the bounce -- what the reference's getState(Positions | Velocities) returns at :283 / :576."""
+        n = self.context.num_atoms
+        x, v = np.zeros((n, 3)), np.zeros((n, 3))
+        dp = C.POINTER(C.c_double)
+        L.check(L.lib.seekr2_b200_fetch_snapshot(self._handle, record.anchor, record.snapshot, x.ctypes.data_as(dp),
+                                                 v.ctypes.data_as(dp), self.context.stream_ptr))
+        return x, v
+
+    def _save_states(self, records) -> None:
+        if not self.saveStateFileName:
+            return
+        seen = set()
+        for r in records:
+            if r.snapshot <= 0:
+                continue
+            # Elber: one state per ending step, named after the last surface of that step (:565, :578)
+            key = (r.anchor, r.snapshot)
+            if key in seen:
+                continue
+            seen.add(key)
+            x, v = self.fetchCrossingState(r)
+            dp = C.POINTER(C.c_double)
+            box = self.context.system.getDefaultPeriodicBoxVectors() if hasattr(self.context.system, "getDefaultPeriodicBoxVectors") else None
+            boxp = None
+            if box is not None:
+                boxa = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+                boxp = boxa.ctypes.data_as(dp)
+            L.check(L.lib.seekr2_b200_write_state_xml(self.stateFileName(r).encode(), x.shape[0], x.ctypes.data_as(dp),
+                                                      v.ctypes.data_as(dp), float(r.time), boxp))
 
     @staticmethod
     def _copy_record(r: L.Record) -> L.Record:

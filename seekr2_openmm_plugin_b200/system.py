@@ -27,6 +27,13 @@ class System:
         self._masses: List[float] = []
         self._forces: list = []
         self._constraints: list = []
+        self._box = np.array([[2.0, 0, 0], [0, 2.0, 0], [0, 0, 2.0]])     # OpenMM's default box
+
+    def getDefaultPeriodicBoxVectors(self) -> np.ndarray:
+        return self._box.copy()
+
+    def setDefaultPeriodicBoxVectors(self, a, b, c) -> None:
+        self._box = np.array([a, b, c], dtype=np.float64).reshape(3, 3)
 
     def addParticle(self, mass: float) -> int:
         self._masses.append(float(mass))
