@@ -2,8 +2,8 @@
 #define B200_SEEKR2_KERNELS_H_
 /* OpenMM KernelImpls over the B200 C ABI.  Drop-in counterparts of
  * CudaIntegrateMmvtLangevinStepKernel / CudaIntegrateElberLangevinStepKernel
- * (seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.h:46-160).  NOT COMPILED in this environment
- * (OpenMM absent) -- see platforms/b200/README.md. */
+ * (seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.h:46-160).  OpenMM is absent from this environment: the
+ * adapter is compiled and exercised against tests/openmm_shim only -- see platforms/b200/README.md. */
 #include "Seekr2Kernels.h"
 #include "openmm/cuda/CudaContext.h"
 #include "seekr2_b200.h"
@@ -27,11 +27,11 @@ protected:
     explicit B200StepKernelBase(OpenMM::CudaContext& cu) : cu(cu) {}
     ~B200StepKernelBase();
     void create(const OpenMM::System& system, seekr2_b200_config& cfg, int seed);
-    std::string mmvtOutput, mmvtStats;
     std::string saveStateFileName;               /* empty = crossing states are not kept */
-    std::vector<int32_t> mmvtGroups;
+    bool stateNameHasCounter = true;
     seekr2_b200_buffers buffers();
     void check(int status) const;                 /* non-zero status -> OpenMMException(last_error) */
+    void updateParams(double temperature, double friction, double stepSize);
     void stepTwoPass(double temperature, double friction, double stepSize, double tolerance);
     void stepMiddle(double temperature, double friction, double stepSize, double tolerance);
     void allocateScratch(bool oldVelm, bool oldDelta);
@@ -44,41 +44,39 @@ protected:
     std::vector<seekr2_b200_record> records;
 };
 
-class B200IntegrateMmvtLangevinStepKernel : public IntegrateMmvtLangevinStepKernel, private B200StepKernelBase {
+/* One implementation per method, instantiated for the plain and the LangevinMiddle integrator
+ * (Seekr2Kernels.h:53-172): MIDDLE selects scheme = SEEKR2_B200_SCHEME_MIDDLE and the three-pass call sequence
+ * kick / middle_drift / finish of CudaSeekr2Kernels.cpp:762-802 instead of kick / finish. */
+template <class KERNEL, class INTEGRATOR, bool MIDDLE>
+class B200MmvtStepKernel : public KERNEL, private B200StepKernelBase {
 public:
-    B200IntegrateMmvtLangevinStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu)
-        : IntegrateMmvtLangevinStepKernel(name, platform), B200StepKernelBase(cu) {}
-    void initialize(const OpenMM::System& system, const MmvtLangevinIntegrator& integrator) override;
-    void execute(OpenMM::ContextImpl& context, const MmvtLangevinIntegrator& integrator) override;
-    double computeKineticEnergy(OpenMM::ContextImpl& context, const MmvtLangevinIntegrator& integrator) override;
+    B200MmvtStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu) : KERNEL(name, platform), B200StepKernelBase(cu) {}
+    void initialize(const OpenMM::System& system, const INTEGRATOR& integrator) override;
+    void execute(OpenMM::ContextImpl& context, const INTEGRATOR& integrator) override;
+    double computeKineticEnergy(OpenMM::ContextImpl& context, const INTEGRATOR& integrator) override;
 private:
     std::string outputFileName, saveStatisticsFileName;
     std::vector<int32_t> milestoneGroups;
+    double expectedTime = 0.0;       /* the device clock, as long as nobody called context.setTime() */
 };
 
-class B200IntegrateElberLangevinStepKernel : public IntegrateElberLangevinStepKernel, private B200StepKernelBase {
+template <class KERNEL, class INTEGRATOR, bool MIDDLE>
+class B200ElberStepKernel : public KERNEL, private B200StepKernelBase {
 public:
-    B200IntegrateElberLangevinStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu)
-        : IntegrateElberLangevinStepKernel(name, platform), B200StepKernelBase(cu) {}
-    void initialize(const OpenMM::System& system, const ElberLangevinIntegrator& integrator) override;
-    void execute(OpenMM::ContextImpl& context, const ElberLangevinIntegrator& integrator) override;
-    double computeKineticEnergy(OpenMM::ContextImpl& context, const ElberLangevinIntegrator& integrator) override;
+    B200ElberStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu) : KERNEL(name, platform), B200StepKernelBase(cu) {}
+    void initialize(const OpenMM::System& system, const INTEGRATOR& integrator) override;
+    void execute(OpenMM::ContextImpl& context, const INTEGRATOR& integrator) override;
+    double computeKineticEnergy(OpenMM::ContextImpl& context, const INTEGRATOR& integrator) override;
 private:
     std::string outputFileName;
     std::vector<int32_t> labels;     /* source groups then destination groups */
     int numSrc = 0;
 };
 
-/* LangevinMiddle twins (Seekr2Kernels.h:115-172; CudaSeekr2Kernels.cpp:604-1177): same engine with
- * scheme = SEEKR2_B200_SCHEME_MIDDLE and the three-pass call sequence kick / middle_drift / finish. */
-class B200IntegrateMmvtLangevinMiddleStepKernel : public IntegrateMmvtLangevinMiddleStepKernel, private B200StepKernelBase {
-public:
-    B200IntegrateMmvtLangevinMiddleStepKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu)
-        : IntegrateMmvtLangevinMiddleStepKernel(name, platform), B200StepKernelBase(cu) {}
-    void initialize(const OpenMM::System& system, const MmvtLangevinMiddleIntegrator& integrator) override;
-    void execute(OpenMM::ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) override;
-    double computeKineticEnergy(OpenMM::ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) override;
-};
+typedef B200MmvtStepKernel<IntegrateMmvtLangevinStepKernel, MmvtLangevinIntegrator, false> B200IntegrateMmvtLangevinStepKernel;
+typedef B200MmvtStepKernel<IntegrateMmvtLangevinMiddleStepKernel, MmvtLangevinMiddleIntegrator, true> B200IntegrateMmvtLangevinMiddleStepKernel;
+typedef B200ElberStepKernel<IntegrateElberLangevinStepKernel, ElberLangevinIntegrator, false> B200IntegrateElberLangevinStepKernel;
+typedef B200ElberStepKernel<IntegrateElberLangevinMiddleStepKernel, ElberLangevinMiddleIntegrator, true> B200IntegrateElberLangevinMiddleStepKernel;
 
 }  // namespace Seekr2Plugin
 #endif

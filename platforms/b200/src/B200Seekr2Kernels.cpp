@@ -1,5 +1,6 @@
 /* OpenMM KernelImpls over the B200 C ABI: the replacement of
- * seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.cpp:63-599.  NOT COMPILED here (no OpenMM).
+ * seekr2plugin/platforms/cuda/src/CudaSeekr2Kernels.cpp:63-1177.  OpenMM is absent here: compiled and run
+ * against tests/openmm_shim only (oracle/build_shim.sh, tests/test_gpu_openmm_shim.py).
  *
  * Per step the reference does Part1 -> applyConstraints -> Part2 -> computeVirtualSites ->
  * calcForcesAndEnergy(false,true,mask) [blocking readback] -> host crossing block -> mmvtBounce.
@@ -61,13 +62,19 @@ seekr2_b200_buffers B200StepKernelBase::buffers() {
     return b;
 }
 
-void B200StepKernelBase::stepTwoPass(double temperature, double friction, double stepSize, double tolerance) {
-    CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
-    integration.setNextStepSize(stepSize);                         /* :187 */
-    if (temperature != prevTemp || friction != prevFriction || stepSize != prevStepSize) {   /* :188-203 */
+/* CudaSeekr2Kernels.cpp:187-203 (Middle :733-748): step size for OpenMM's constraint kernels, integration
+   parameters for ours; runs before the first-step test, which needs them */
+void B200StepKernelBase::updateParams(double temperature, double friction, double stepSize) {
+    cu.getIntegrationUtilities().setNextStepSize(stepSize);
+    if (temperature != prevTemp || friction != prevFriction || stepSize != prevStepSize) {
         check(seekr2_b200_set_params(handle, temperature, friction, stepSize));
         prevTemp = temperature; prevFriction = friction; prevStepSize = stepSize;
     }
+}
+
+void B200StepKernelBase::stepTwoPass(double temperature, double friction, double stepSize, double tolerance) {
+    CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
+    updateParams(temperature, friction, stepSize);
     seekr2_b200_buffers b = buffers();
     void* stream = (void*) cu.getCurrentStream();
     const int randomIndex = integration.prepareRandomNumbers(cu.getPaddedNumAtoms());       /* :214 */
@@ -86,11 +93,7 @@ void B200StepKernelBase::allocateScratch(bool needOldVelm, bool needOldDelta) {
 /* CudaIntegrateMmvtLangevinMiddleStepKernel::execute, integration part (CudaSeekr2Kernels.cpp:756-802) */
 void B200StepKernelBase::stepMiddle(double temperature, double friction, double stepSize, double tolerance) {
     CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
-    integration.setNextStepSize(stepSize);
-    if (temperature != prevTemp || friction != prevFriction || stepSize != prevStepSize) {   /* :734-748 */
-        check(seekr2_b200_set_params(handle, temperature, friction, stepSize));
-        prevTemp = temperature; prevFriction = friction; prevStepSize = stepSize;
-    }
+    updateParams(temperature, friction, stepSize);
     seekr2_b200_buffers b = buffers();
     b.d_old_velm = (void*) oldVelm.getDevicePointer();
     b.d_old_delta = (void*) oldDelta.getDevicePointer();
@@ -126,130 +129,119 @@ void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::v
         Vec3 a, b, c;
         cu.getPeriodicBoxVectors(a, b, c);
         const double box[9] = {a[0], a[1], a[2], b[0], b[1], b[2], c[0], c[1], c[2]};
-        const std::string name = saveStateFileName + "_" + std::to_string(r.counter) + "_" + std::to_string(label);
+        /* "_<counter>_<group>" (:285-287, :578-580, :838-840); the reference's ElberLangevinMiddle kernel leaves
+           the counter out (:1157) and so do we */
+        const std::string name = saveStateFileName + (stateNameHasCounter ? "_" + std::to_string(r.counter) : std::string()) + "_" + std::to_string(label);
         check(seekr2_b200_write_state_xml(name.c_str(), cu.getNumAtoms(), xo.data(), vo.data(), r.time, box));
     }
 }
 
-/* ---- MMVT ------------------------------------------------------------------------------------------- */
+/* ---- MMVT (CudaSeekr2Kernels.cpp:104-370; Middle :646-919) ------------------------------------------- */
 
-void B200IntegrateMmvtLangevinStepKernel::initialize(const System& system, const MmvtLangevinIntegrator& integrator) {
+template <class K, class I, bool MIDDLE>
+void B200MmvtStepKernel<K, I, MIDDLE>::initialize(const System& system, const I& integrator) {
     seekr2_b200_config cfg{};
     cfg.kind = SEEKR2_B200_KIND_MMVT;
+    cfg.scheme = MIDDLE ? SEEKR2_B200_SCHEME_MIDDLE : SEEKR2_B200_SCHEME_LANGEVIN;
     cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
     const int32_t counter0 = integrator.getBounceCounter();        /* :151 */
     cfg.bounce_counter0 = &counter0;
     saveStateFileName = integrator.getSaveStateFileName();          /* :135-139 */
     create(system, cfg, integrator.getRandomNumberSeed());
+    if (MIDDLE) allocateScratch(true, true);
     outputFileName = integrator.getOutputFileName();
     saveStatisticsFileName = integrator.getSaveStatisticsFileName();
     for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) milestoneGroups.push_back(integrator.getMilestoneGroup(i));
     check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, outputFileName.c_str()));          /* :158-171 */
 }
 
-void B200IntegrateMmvtLangevinStepKernel::execute(ContextImpl& context, const MmvtLangevinIntegrator& integrator) {
+template <class K, class I, bool MIDDLE>
+void B200MmvtStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& integrator) {
     cu.setAsCurrent();
+    void* stream = (void*) cu.getCurrentStream();
+    if (cu.getTime() != expectedTime)                              /* someone called context.setTime(): follow it */
+        check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), stream));
+    updateParams(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize());
     if (cu.getStepCount() <= 0) {                                  /* :205-210 */
         seekr2_b200_buffers b = buffers();
-        check(seekr2_b200_check_first_step(handle, &b, nullptr, (void*) cu.getCurrentStream()));
+        check(seekr2_b200_check_first_step(handle, &b, nullptr, stream));
     }
-    stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    if (MIDDLE) stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    else stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     drainTo(outputFileName, SEEKR2_B200_KIND_MMVT, milestoneGroups, 0);
     if (!saveStatisticsFileName.empty() && !records.empty()) {     /* :313-345 */
         seekr2_b200_anchor_state st;
-        check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+        check(seekr2_b200_get_state(handle, 0, &st, stream));
         check(seekr2_b200_write_statistics(saveStatisticsFileName.c_str(), &st, milestoneGroups.data(), (int32_t) milestoneGroups.size()));
     }
     cu.setTime(cu.getTime() + integrator.getStepSize());           /* :362-365 */
     cu.setStepCount(cu.getStepCount() + 1);
     cu.reorderAtoms();
+    expectedTime = cu.getTime();
 }
 
-double B200IntegrateMmvtLangevinStepKernel::computeKineticEnergy(ContextImpl&, const MmvtLangevinIntegrator& integrator) {
-    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :368-370 */
+template <class K, class I, bool MIDDLE>
+double B200MmvtStepKernel<K, I, MIDDLE>::computeKineticEnergy(ContextImpl&, const I& integrator) {
+    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :368-370, :917-919 */
 }
 
-/* ---- Elber ------------------------------------------------------------------------------------------ */
+/* ---- Elber (CudaSeekr2Kernels.cpp:392-599; Middle :947-1177) ---------------------------------------- */
 
-void B200IntegrateElberLangevinStepKernel::initialize(const System& system, const ElberLangevinIntegrator& integrator) {
+template <class K, class I, bool MIDDLE>
+void B200ElberStepKernel<K, I, MIDDLE>::initialize(const System& system, const I& integrator) {
     seekr2_b200_config cfg{};
     cfg.kind = SEEKR2_B200_KIND_ELBER;
+    cfg.scheme = MIDDLE ? SEEKR2_B200_SCHEME_MIDDLE : SEEKR2_B200_SCHEME_LANGEVIN;
     std::vector<int32_t> src, dest;
     for (int i = 0; i < integrator.getNumSrcMilestoneGroups(); i++) src.push_back(integrator.getSrcMilestoneGroup(i));
     for (int i = 0; i < integrator.getNumDestMilestoneGroups(); i++) dest.push_back(integrator.getDestMilestoneGroup(i));
+    /* :415-436 -- the reference's own check and message, on every force of the System (not only the typed ones) */
+    for (const std::vector<int32_t>* list : {&src, &dest})
+        for (int32_t group : *list) {
+            bool found = false;
+            for (int j = 0; j < system.getNumForces(); j++) found = found || system.getForce(j).getForceGroup() == group;
+            if (!found) throw OpenMMException("System contains no force groups used to detect Elber boundary crossings. Check for mismatches between force group assignments and the groups added to the Elber integrator.");
+        }
     cfg.num_src = (int) src.size(); cfg.src_groups = src.data();
     cfg.num_dest = (int) dest.size(); cfg.dest_groups = dest.data();
     cfg.end_on_src_milestone = integrator.getEndOnSrcMilestone();  /* :414 */
     const int32_t counter0 = integrator.getCrossingCounter();      /* :403 */
     cfg.crossing_counter0 = &counter0;
     saveStateFileName = integrator.getSaveStateFileName();          /* :405-409 */
-    create(system, cfg, integrator.getRandomNumberSeed());          /* missing force group -> the reference's message (:421-422) */
+    stateNameHasCounter = !MIDDLE;                                  /* :1157 vs :578-580 */
+    create(system, cfg, integrator.getRandomNumberSeed());
+    if (MIDDLE) allocateScratch(false, true);
     outputFileName = integrator.getOutputFileName();
     labels = src; labels.insert(labels.end(), dest.begin(), dest.end());
     numSrc = (int) src.size();
     check(seekr2_b200_write_header(SEEKR2_B200_KIND_ELBER, outputFileName.c_str()));         /* :447-462 */
 }
 
-void B200IntegrateElberLangevinStepKernel::execute(ContextImpl& context, const ElberLangevinIntegrator& integrator) {
+template <class K, class I, bool MIDDLE>
+void B200ElberStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& integrator) {
     cu.setAsCurrent();
+    void* stream = (void*) cu.getCurrentStream();
     /* Elber's crossing test looks at the context time (:533,:558) and may reset it (:545): the engine
        keeps that clock on the device; mirror OpenMM's copy into it before and out of it after */
-    check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), (void*) cu.getCurrentStream()));
-    stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), stream));
+    if (MIDDLE) stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
+    else stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     drainTo(outputFileName, SEEKR2_B200_KIND_ELBER, labels, numSrc);
     seekr2_b200_anchor_state st;
-    check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+    check(seekr2_b200_get_state(handle, 0, &st, stream));
     cu.setTime(st.time);                                           /* already advanced by stepSize (:592) */
     cu.setStepCount(cu.getStepCount() + 1);
     cu.reorderAtoms();
 }
 
-double B200IntegrateElberLangevinStepKernel::computeKineticEnergy(ContextImpl&, const ElberLangevinIntegrator& integrator) {
-    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :597-599 */
+template <class K, class I, bool MIDDLE>
+double B200ElberStepKernel<K, I, MIDDLE>::computeKineticEnergy(ContextImpl&, const I& integrator) {
+    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :597-599, :1175-1177 */
 }
 
-/* ---- MMVT, LangevinMiddle ---------------------------------------------------------------------------- */
-
-void B200IntegrateMmvtLangevinMiddleStepKernel::initialize(const System& system, const MmvtLangevinMiddleIntegrator& integrator) {
-    seekr2_b200_config cfg{};
-    cfg.kind = SEEKR2_B200_KIND_MMVT;
-    cfg.scheme = SEEKR2_B200_SCHEME_MIDDLE;
-    cfg.num_milestone_groups = integrator.getNumMilestoneGroups();
-    const int32_t counter0 = integrator.getBounceCounter();
-    cfg.bounce_counter0 = &counter0;
-    saveStateFileName = integrator.getSaveStateFileName();
-    create(system, cfg, integrator.getRandomNumberSeed());
-    allocateScratch(true, true);
-    mmvtOutput = integrator.getOutputFileName();
-    mmvtStats = integrator.getSaveStatisticsFileName();
-    for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) mmvtGroups.push_back(integrator.getMilestoneGroup(i));
-    check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, mmvtOutput.c_str()));
-}
-
-void B200IntegrateMmvtLangevinMiddleStepKernel::execute(ContextImpl& context, const MmvtLangevinMiddleIntegrator& integrator) {
-    cu.setAsCurrent();
-    if (cu.getStepCount() <= 0) {                                  /* :750-755 */
-        seekr2_b200_buffers b = buffers();
-        check(seekr2_b200_check_first_step(handle, &b, nullptr, (void*) cu.getCurrentStream()));
-    }
-    stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
-    drainTo(mmvtOutput, SEEKR2_B200_KIND_MMVT, mmvtGroups, 0);
-    if (!mmvtStats.empty() && !records.empty()) {
-        seekr2_b200_anchor_state st;
-        check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
-        check(seekr2_b200_write_statistics(mmvtStats.c_str(), &st, mmvtGroups.data(), (int32_t) mmvtGroups.size()));
-    }
-    cu.setTime(cu.getTime() + integrator.getStepSize());           /* :911-914 */
-    cu.setStepCount(cu.getStepCount() + 1);
-    cu.reorderAtoms();
-}
-
-double B200IntegrateMmvtLangevinMiddleStepKernel::computeKineticEnergy(ContextImpl&, const MmvtLangevinMiddleIntegrator& integrator) {
-    return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());
-}
-
-/* ElberLangevinMiddle: identical to B200IntegrateElberLangevinStepKernel with cfg.scheme = MIDDLE and
-   stepMiddle() in place of stepTwoPass() (CudaSeekr2Kernels.cpp:1032-1173); left to the maintainer who
-   can compile against OpenMM -- every C-ABI entry point it needs is exercised by tests/test_gpu_middle.py. */
+template class B200MmvtStepKernel<IntegrateMmvtLangevinStepKernel, MmvtLangevinIntegrator, false>;
+template class B200MmvtStepKernel<IntegrateMmvtLangevinMiddleStepKernel, MmvtLangevinMiddleIntegrator, true>;
+template class B200ElberStepKernel<IntegrateElberLangevinStepKernel, ElberLangevinIntegrator, false>;
+template class B200ElberStepKernel<IntegrateElberLangevinMiddleStepKernel, ElberLangevinMiddleIntegrator, true>;
 
 }  // namespace Seekr2Plugin

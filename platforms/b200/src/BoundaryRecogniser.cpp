@@ -1,6 +1,7 @@
 /* Walks the System's CustomCentroidBondForce objects and emits the typed boundary descriptors of
  * include/seekr2_b200.h.  Same recognition rules as the Python harness
- * (seekr2_openmm_plugin_b200/system.py::_recognise), which IS tested.  NOT COMPILED here (no OpenMM). */
+ * (seekr2_openmm_plugin_b200/system.py::_recognise), which is tested on its own; this file is
+ * compiled and run against tests/openmm_shim only (OpenMM is absent here). */
 #include "B200Seekr2Kernels.h"
 #include "openmm/CustomCentroidBondForce.h"
 #include "openmm/OpenMMException.h"

@@ -322,12 +322,14 @@ class _B200LangevinBase:
         return new
 
     def stateFileName(self, record: L.Record) -> str:
-        """``saveStateFileName + "_" + counter + "_" + milestoneGroup`` (CudaSeekr2Kernels.cpp:285-287, :578-580)."""
+        """``saveStateFileName + "_" + counter + "_" + milestoneGroup`` (CudaSeekr2Kernels.cpp:285-287, :578-580, :838-840)."""
         labels = self._labels(record.anchor)
         idx = record.index + (self._num_src() if record.kind in (L.REC_ELBER_DEST, L.REC_ELBER_DEST_STAR) else 0)
         prefix = self.saveStateFileName
         if self.context is not None and self.context.num_anchors > 1:
             prefix = f"{prefix}.{record.anchor}"
+        if self.KIND == L.KIND_ELBER and self.SCHEME == L.SCHEME_MIDDLE:
+            return f"{prefix}_{labels[idx]}"        # the ElberLangevinMiddle kernel leaves the counter out (:1157)
         return f"{prefix}_{record.counter}_{labels[idx]}"
 
     def fetchCrossingState(self, record: L.Record):

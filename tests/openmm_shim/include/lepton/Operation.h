@@ -1,0 +1,1 @@
+/* openmm_shim: the plugin headers include Lepton but never use it */

@@ -1,0 +1,2 @@
+/* openmm_shim (NOT OpenMM): see ShimCore.h */
+#include "openmm/ShimCore.h"

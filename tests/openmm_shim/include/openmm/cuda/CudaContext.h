@@ -1,0 +1,2 @@
+/* openmm_shim (NOT OpenMM): see ShimCuda.h */
+#include "openmm/cuda/ShimCuda.h"
