@@ -302,9 +302,14 @@ def main() -> None:
     A_saved, A = A, 1
     ctx1, integ1, _ = make_context("mmvt")
     t1, k1, n1, _ = timed_run(ctx1, integ1, args.steps, W)
-    single_anchor = {"ns_per_day_per_anchor": ns_per_day(args.steps / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / args.steps,
-                     "note": "1 anchor per GPU, L2-resident, launch-latency bound; CUDA graph of 32 steps"}
     del ctx1, integ1
+    ctx1, integ1, _ = make_context("langevin")
+    t1l, k1l, n1l, _ = timed_run(ctx1, integ1, args.steps, W)
+    del ctx1, integ1
+    single_anchor = {"ns_per_day_per_anchor": ns_per_day(args.steps / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / args.steps,
+                     "plain_langevin_us_per_step": t1l * 1e3 / args.steps, "mmvt_over_plain_langevin": t1 / t1l,
+                     "note": "1 anchor per GPU, L2-resident, launch-latency bound (the CV -> decision -> store chain is "
+                             "serial inside the launch); CUDA graph of 32 steps"}
     A = A_saved
 
     # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---

@@ -338,7 +338,7 @@ int seekr2_b200_append_records(int32_t kind, const char* path, const seekr2_b200
 int seekr2_b200_write_statistics(const char* path, const seekr2_b200_anchor_state* st,
                                  const int32_t* labels, int32_t num_labels);
 
-/* debug: when d_probe (int64[8*A + 4], device) is set the fused kernel records %globaltimer stamps of
+/* debug: when d_probe (int64[8*A + 4 + 16], device) is set the fused kernel records %globaltimer stamps of
    each decide block ([0] start, [1] loads returned, [2] atoms advanced, [3] accumulated, [4] groups
    reduced, [5] decision published, [6] earliest streaming arrival of the anchor) and the streaming
    blocks' total wait ([8A..]: blocks that waited, polls, ns).  NULL disables it.                     */

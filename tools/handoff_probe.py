@@ -13,7 +13,7 @@ integ = H.make_mmvt_integrator(syn, "")
 ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
 ctx.setPositions(positions); ctx.setVelocities(syn.velocities)
 integ.step(8)
-probe = torch.zeros(8 * A + 4, dtype=torch.int64, device="cuda")
+probe = torch.zeros(8 * A + 4 + 16, dtype=torch.int64, device="cuda")
 big = torch.iinfo(torch.int64).max
 for it in range(3):
     probe.zero_(); probe[6:8 * A:8] = big
@@ -28,4 +28,8 @@ for it in range(3):
     print(f"iter {it}: " + "; ".join(f"{n} {np.median(d[:, i] - t0):.0f}" for i, n in enumerate(names)) + " (median ns over anchors)")
     print(f"   streaming blocks that waited {p[8*A]}, polls {p[8*A+1]}, total wait {p[8*A+2]/1e3:.1f} us "
           f"(mean {p[8*A+2]/max(1,p[8*A]):.0f} ns per waiting block)")
+    cyc = p[8 * A + 4: 8 * A + 4 + 11]
+    stages = ["step index loaded", "gathers issued", "gathers back", "cleared+sync", "advanced", "accumulated", "all warps reduced",
+              "boundary terms", "published", "bookkeeping+slab+clock"]
+    print("   anchor 0 decide block, SM cycles since block start: " + "; ".join(f"{n} {int(cyc[i + 1] - cyc[0])}" for i, n in enumerate(stages)))
 L.check(L.lib.seekr2_b200_debug_set_probe(integ._handle, None))
