@@ -47,6 +47,7 @@ struct EngineDev {
     int* head_start;             // [2] decide blocks that have issued their gathers (per launch parity)
     int first_wave_blocks;       // streaming blocks resident at kernel start (they wait for head_start)
     int head_start_target;       // A x warps per decide block that hold group slots
+    int prefetch_ahead;          // first-wave blocks prefetch the tile of block (own + this) into L2 while they wait (0 = off)
     int* flags;                  // [2][A] decision hand-off of the fused kernel: 0 = not yet; bit0 valid, bit1 bounce,
                                  // bit2 save the advanced state into snapshot slot (flag >> 4)
     int snap_slots;              // save_state_slots (0 = off)

@@ -394,6 +394,8 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         if (const char* hs = getenv("SEEKR2_B200_HEAD_START")) if (hs[0] == '0') d.first_wave_blocks = 0;   // tuning knob
         const int slot_warps = ((num_slots < kThreads ? num_slots : kThreads) + 31) / 32;
         d.head_start_target = A * slot_warps;
+        d.prefetch_ahead = d.first_wave_blocks;
+        if (const char* pf = getenv("SEEKR2_B200_PREFETCH")) if (pf[0] == '0') d.prefetch_ahead = 0;               // tuning knob
     }
     *out = h;
     return SEEKR2_B200_OK;
