@@ -154,6 +154,16 @@ def main() -> None:
     ap.add_argument("--no-box", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner,
+    # torch warnings) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +188,7 @@ def main() -> None:
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "anchor-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -189,8 +199,7 @@ def main() -> None:
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's banner / logs never go to stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     A = args.anchors
@@ -285,8 +294,9 @@ def main() -> None:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this very
-    # workload (profiles/r01_fused_step_ncu_full.txt: 260.2 MB read + 135.6 MB written); null otherwise
-    traffic = 395.8e6 if (A, args.atoms) == (128, N_ATOMS) else None
+    # workload (profiles/r01b_fused_step_ncu_full.txt: 260.2 MB read + 133.4 MB written; the tail of the writes is
+    # still in L2 when the kernel ends); null otherwise
+    traffic = 393.6e6 if (A, args.atoms) == (128, N_ATOMS) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
@@ -385,7 +395,7 @@ def main() -> None:
                 "mmvt_over_plain_langevin": mmvt_over_langevin, "single_anchor_per_gpu": single_anchor, "box_100k": box,
                 "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
                 "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
