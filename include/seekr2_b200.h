@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 5
+#define SEEKR2_B200_ABI_VERSION 6
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -300,11 +300,23 @@ int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream);
 
 /* ---- results ---------------------------------------------------------------------------------- */
 
-/* copy the crossing records appended since the previous drain (all anchors, anchor-major, each
-   anchor's records in order) to `out`; *out_n = number written.  Synchronises `stream`.
-   Returns SEEKR2_B200_ERR_RING_OVERFLOW if records were lost.                                      */
+/* The crossing log of the reference is appended inside execute() (CudaSeekr2Kernels.cpp:257-311); here records
+   wait in a per-anchor device ring and are drained ASYNCHRONOUSLY:
+     drain_begin  enqueues, on `stream`, one small kernel that packs every record appended since the previous drain
+                  (all anchors, anchor-major, each anchor's records in order, at most max_records and at most 65536)
+                  straight into mapped pinned host memory, plus an event; it returns at once and further steps may be
+                  queued behind it;
+     drain_end    waits for that event only (never for work queued after drain_begin), copies the records to `out`,
+                  *out_n = number written, *out_waiting (optional) = records still in the rings (call again).
+   Returns SEEKR2_B200_ERR_RING_OVERFLOW from drain_end if a ring wrapped over undrained records.  One drain in
+   flight per engine.                                                                                    */
+int seekr2_b200_drain_begin(seekr2_b200_handle h, int64_t max_records, void* stream);
+int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n,
+                          int64_t* out_waiting);
+/* drain_begin + drain_end: blocks until everything queued on `stream` before the call has run.             */
 int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records,
                       int64_t* out_n, void* stream);
+
 int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anchor_state* out,
                           void* stream);
 /* Context::setTime / setStepCount analogue (used by reinitialize and by tests)                     */

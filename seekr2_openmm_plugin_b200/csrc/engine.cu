@@ -45,6 +45,7 @@ int fail(int code, const char* fmt, ...) {
 
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
+constexpr long long kStageRecords = 1 << 16;   // staging buffer of the asynchronous drain (2.6 MB of mapped pinned memory)
 constexpr double kBoltzmann = 1.380649e-23;
 constexpr double kAvogadro = 6.02214076e23;
 constexpr double kBoltz = (kBoltzmann * kAvogadro) / 1000.0;
@@ -84,7 +85,13 @@ struct seekr2_b200_engine {
     void* d_snap_velm = nullptr;
     // host mirrors for drain
     AnchorState* h_state = nullptr;           // pinned [A]
-    std::vector<long long> ring_tail;         // records already drained, per anchor
+    // asynchronous drain: device-side tails, pack scratch, staging buffer + header in mapped pinned host memory
+    long long* d_ring_tail = nullptr;         // [A] records already drained, per anchor
+    long long* d_pack_scratch = nullptr;      // [3 A]
+    Record* h_stage = nullptr;                // [kStageRecords], written by ring_pack_kernel over PCIe
+    long long* h_stage_hdr = nullptr;         // [4]
+    cudaEvent_t drain_event = nullptr;
+    bool drain_pending = false;
     // graph capture
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -232,6 +239,10 @@ int seekr2_b200_destroy(seekr2_b200_handle h) {
     cudaFree(h->d_decision); cudaFree(h->d_flags); cudaFree(h->d_step_shadow);
     cudaFree(h->d_snap_posq); cudaFree(h->d_snap_corr); cudaFree(h->d_snap_velm);
     if (h->h_state) cudaFreeHost(h->h_state);
+    cudaFree(h->d_ring_tail); cudaFree(h->d_pack_scratch);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_stage_hdr) cudaFreeHost(h->h_stage_hdr);
+    if (h->drain_event) cudaEventDestroy(h->drain_event);
     delete h;
     return SEEKR2_B200_OK;
 }
@@ -368,7 +379,13 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         h->h_state[a].crossing_counter = cfg->crossing_counter0 ? cfg->crossing_counter0[a] : 0;
     }
     CREATE_TRY(cudaMemcpy(h->d_state, h->h_state, sizeof(AnchorState) * A, cudaMemcpyHostToDevice));
-    h->ring_tail.assign(A, 0);
+    CREATE_TRY(cudaMalloc(&h->d_ring_tail, sizeof(long long) * A));
+    CREATE_TRY(cudaMemset(h->d_ring_tail, 0, sizeof(long long) * A));
+    CREATE_TRY(cudaMalloc(&h->d_pack_scratch, sizeof(long long) * 3 * A));
+    CREATE_TRY(cudaHostAlloc(&h->h_stage, sizeof(Record) * kStageRecords, cudaHostAllocMapped));
+    CREATE_TRY(cudaHostAlloc(&h->h_stage_hdr, sizeof(long long) * 4, cudaHostAllocMapped));
+    memset(h->h_stage_hdr, 0, sizeof(long long) * 4);
+    CREATE_TRY(cudaEventCreateWithFlags(&h->drain_event, cudaEventDisableTiming));
 
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
@@ -548,37 +565,53 @@ int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream) {
     return SEEKR2_B200_OK;
 }
 
-int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n, void* stream) {
-    if (!h || !out_n) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+// Asynchronous drain (north star: "a device ring buffer drained asynchronously").  begin() only enqueues the pack
+// kernel and an event on `stream` and returns; the caller may queue further steps behind it.  end() waits for that
+// event alone -- not for anything queued later -- and hands out the records, already in host memory.
+int seekr2_b200_drain_begin(seekr2_b200_handle h, int64_t max_records, void* stream) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
     if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "drain cannot be captured");
+    if (h->drain_pending) return fail(SEEKR2_B200_ERR_INVALID, "a drain is already in flight: call seekr2_b200_drain_end first");
+    if (max_records < 0) return fail(SEEKR2_B200_ERR_INVALID, "negative max_records");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
-    const int A = h->cfg.num_anchors;
-    const int cap = h->dev.ring_capacity;
-    *out_n = 0;
-    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(AnchorState) * A, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    bool overflow = false;
-    int64_t n = 0;
-    for (int a = 0; a < A; a++) {
-        long long head = h->h_state[a].ring_head, tail = h->ring_tail[a];
-        if (head - tail > cap) { overflow = true; tail = head - cap; }
-        while (tail < head) {
-            const long long pos = tail % cap;
-            long long chunk = head - tail;
-            if (chunk > cap - pos) chunk = cap - pos;
-            if (n + chunk > max_records) { chunk = max_records - n; }
-            if (chunk <= 0) break;
-            if (!out) return fail(SEEKR2_B200_ERR_INVALID, "null record buffer");
-            CUDA_TRY(cudaMemcpyAsync(out + n, h->d_ring + (size_t) a * cap + pos, sizeof(Record) * chunk, cudaMemcpyDeviceToHost, s));
-            n += chunk; tail += chunk;
-        }
-        h->ring_tail[a] = tail;
-    }
-    CUDA_TRY(cudaStreamSynchronize(s));
-    *out_n = n;
-    if (overflow) return fail(SEEKR2_B200_ERR_RING_OVERFLOW, "crossing ring overflowed: records were lost; drain more often or raise ring_capacity");
+    Record* d_stage = nullptr;
+    long long* d_hdr = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer((void**) &d_stage, h->h_stage, 0));
+    CUDA_TRY(cudaHostGetDevicePointer((void**) &d_hdr, h->h_stage_hdr, 0));
+    const long long limit = max_records < kStageRecords ? max_records : kStageRecords;
+    ring_pack_kernel<<<1, 1024, 0, s>>>(h->dev, h->d_ring_tail, h->d_pack_scratch, d_stage, d_hdr, limit);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->drain_event, s));
+    h->drain_pending = true;
     return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n, int64_t* out_waiting) {
+    if (!h || !out_n) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    if (!h->drain_pending) return fail(SEEKR2_B200_ERR_INVALID, "no drain in flight: call seekr2_b200_drain_begin first");
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaEventSynchronize(h->drain_event));
+    h->drain_pending = false;
+    const long long n = h->h_stage_hdr[0];
+    *out_n = 0;
+    if (out_waiting) *out_waiting = h->h_stage_hdr[2];
+    if (n > max_records) return fail(SEEKR2_B200_ERR_INVALID, "record buffer smaller than the max_records given to seekr2_b200_drain_begin");
+    if (n > 0) {
+        if (!out) return fail(SEEKR2_B200_ERR_INVALID, "null record buffer");
+        memcpy(out, h->h_stage, sizeof(Record) * (size_t) n);
+    }
+    *out_n = n;
+    if (h->h_stage_hdr[1]) return fail(SEEKR2_B200_ERR_RING_OVERFLOW, "crossing ring overflowed: records were lost; drain more often or raise ring_capacity");
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n, void* stream) {
+    if (!h || !out_n) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    *out_n = 0;
+    const int rc = seekr2_b200_drain_begin(h, max_records, stream);
+    if (rc != SEEKR2_B200_OK) return rc;
+    return seekr2_b200_drain_end(h, out, max_records, out_n, nullptr);
 }
 
 int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anchor_state* out, void* stream) {

@@ -50,6 +50,7 @@ class _B200LangevinBase:
         self.stepsPerGraph = 32
         self.ringCapacity = 0
         self.saveStateSlots = 32       # crossing states kept on the device between drains (saveStateFileName set)
+        self.drainInterval = 4096      # steps between asynchronous drains inside one step(n) call
         self.useRandomPool = False     # True: Gaussian pool refilled by a harness kernel (OpenMM style)
         self.rngAnchorBase = 0         # global index of the context's first anchor (multi-GPU runs)
         self._steps_issued = 0
@@ -227,15 +228,16 @@ class _B200LangevinBase:
             ctx.groups_dirty = True
 
     def step(self, steps: int) -> None:
+        """``Integrator::step(n)``.  The n steps are queued in chunks of ``drainInterval``; after each chunk an
+        asynchronous drain is queued behind it (``seekr2_b200_drain_begin``) and the NEXT chunk is queued before the
+        host collects that drain, so appending to the crossings file overlaps the GPU's work on the next chunk and
+        the rings never overflow however large n is.  With a state file name set the chunk is ``saveStateSlots``
+        steps and each drain is collected at once: a step saves at most one crossing state per anchor, so none can
+        be overwritten before it is fetched (the reference writes the file inside the step,
+        CudaSeekr2Kernels.cpp:282-293)."""
         if self.context is None:
             raise L.Seekr2Error(L.ERR_INVALID, "This Integrator is not bound to a context!")
         ctx = self.context
-        if self.saveStateFileName and self.KIND != L.KIND_LANGEVIN and steps > self.saveStateSlots:
-            # a step saves at most one crossing state per anchor, so draining every `slots` steps can
-            # never lose one (the reference writes the file inside the step, CudaSeekr2Kernels.cpp:282-293)
-            for first in range(0, steps, self.saveStateSlots):
-                self.step(min(self.saveStateSlots, steps - first))
-            return
         self._update_params()
         if self.stepMode == "two_pass":
             middle = self.SCHEME == L.SCHEME_MIDDLE
@@ -243,6 +245,29 @@ class _B200LangevinBase:
         ctx.prepareForces()
         self._first_step_check()
         self._before_first_step()
+        saving = bool(self.saveStateFileName) and self.KIND != L.KIND_LANGEVIN
+        chunk = max(1, self.saveStateSlots if saving else self.drainInterval)
+        done, pending, new = 0, False, []
+        while done < steps:
+            n = min(chunk, steps - done)
+            self._issue(n)
+            done += n
+            if self.KIND == L.KIND_LANGEVIN:
+                continue
+            if pending:
+                new += self._drain_collect()          # the previous chunk's records; the GPU is busy with this chunk
+            self._drain_begin()
+            pending = True
+            if saving:
+                new += self._drain_collect()
+                pending = False
+        if pending:
+            new += self._drain_collect()
+        self._after_steps(new)
+
+    def _issue(self, steps: int) -> None:
+        """Queue ``steps`` steps on the context's stream (graph replays where possible); never blocks."""
+        ctx = self.context
         done = 0
         if self.useGraph and self.stepMode == "fused":
             S = self.stepsPerGraph
@@ -264,7 +289,6 @@ class _B200LangevinBase:
             ctx.random_cursor += 1
             self._steps_issued += 1
             done += 1
-        self._after_steps()
 
     def _capture(self, S: int, random_index0: int) -> None:
         ctx = self.context
@@ -285,15 +309,18 @@ class _B200LangevinBase:
     def _first_step_check(self) -> None:
         pass
 
-    def _after_steps(self) -> None:
-        self.drain()
+    def _after_steps(self, new) -> None:
+        pass
 
     # -- results -------------------------------------------------------------------------------------
     _DRAIN_CHUNK = 1 << 14
 
-    def drain(self) -> List[L.Record]:
-        """Fetch new crossing records and append them to the output file(s)."""
-        ctx = self.context
+    def _drain_begin(self) -> None:
+        L.check(L.lib.seekr2_b200_drain_begin(self._handle, self._DRAIN_CHUNK, self.context.stream_ptr))
+
+    def _drain_collect(self) -> List[L.Record]:
+        """Collect the drain in flight (and whatever did not fit into it), append the records to the output
+        file(s), write the crossing states.  Waits only for the work queued before ``_drain_begin``."""
         if getattr(self, "_drain_buf", None) is None:
             self._drain_buf = (L.Record * self._DRAIN_CHUNK)()
         buf = self._drain_buf
@@ -301,8 +328,8 @@ class _B200LangevinBase:
         new: List[L.Record] = []
         status = L.OK
         while True:
-            n = C.c_int64(0)
-            rc = L.lib.seekr2_b200_drain(self._handle, buf, self._DRAIN_CHUNK, C.byref(n), ctx.stream_ptr)
+            n, waiting = C.c_int64(0), C.c_int64(0)
+            rc = L.lib.seekr2_b200_drain_end(self._handle, buf, self._DRAIN_CHUNK, C.byref(n), C.byref(waiting))
             if rc not in (L.OK, L.ERR_RING_OVERFLOW):
                 L.check(rc)
             status = status or rc
@@ -313,13 +340,19 @@ class _B200LangevinBase:
                     labels = self._labels(a)
                     L.check(L.lib.seekr2_b200_append_records(self.KIND, names[a].encode(), buf, n.value, a,
                                                              _i32_array(labels), len(labels), self._num_src()))
-            if n.value < self._DRAIN_CHUNK:
+            if waiting.value <= 0:
                 break
+            self._drain_begin()
         self._records.extend(new)
         self._save_states(new)
         if status != L.OK:
             raise L.Seekr2Error(status, "crossing ring overflowed: records were lost; drain more often or raise ringCapacity")
         return new
+
+    def drain(self) -> List[L.Record]:
+        """Fetch new crossing records and append them to the output file(s) (blocks until every queued step ran)."""
+        self._drain_begin()
+        return self._drain_collect()
 
     def stateFileName(self, record: L.Record) -> str:
         """``saveStateFileName + "_" + counter + "_" + milestoneGroup`` (CudaSeekr2Kernels.cpp:285-287, :578-580, :838-840)."""
@@ -444,8 +477,7 @@ class MmvtLangevinIntegrator(_B200LangevinBase):
             ctx.groups_dirty = False
         self._first_checked = self._handle.value
 
-    def _after_steps(self):
-        new = self.drain()
+    def _after_steps(self, new):
         if self.saveStatisticsFileName and new:            # :313-345
             ctx = self.context
             for a in range(ctx.num_anchors):

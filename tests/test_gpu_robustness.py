@@ -128,3 +128,56 @@ def test_long_run_statistics_in_kernel_rng_vs_oracle(cuda_device):
         assert abs(rate_g - rate_c) < 5 * sigma, (i, rate_g, rate_c, sigma)
         inc_g, inc_c = g_r[i] / g_nij[i], c_r[i] / c_nij[i]                  # mean incubation time before a switch
         assert abs(inc_g - inc_c) < 0.25 * inc_c, (i, inc_g, inc_c)
+
+
+def test_asynchronous_drain_pipelined_inside_one_long_step_call(cuda_device, tmp_path):
+    """step(n) queues an asynchronous drain after every `drainInterval` steps and collects it while the next chunk
+    runs: a run that appends many times the ring capacity loses nothing, and file + record list equal the oracle's."""
+    syn = S.ballistic_toy(speed=5.0, dt=0.01)          # bounces every ~4 steps
+    steps = 20000
+    rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, ""), L.MIXED, steps)
+    path = str(tmp_path / "long.txt")
+    integ = H.make_mmvt_integrator(syn, path)
+    integ.ringCapacity = 512
+    integ.drainInterval = 1000
+    integ.setUseGraph(True, 8)
+    hb = H.make_host_buffers(L.MIXED, syn.positions, syn.velocities, syn.masses)
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    H.upload(ctx, [hb])
+    ctx.setRandomPool(np.zeros((steps * 32, 4), dtype=np.float32))
+    integ.step(steps)
+    assert len(o.records()) > 8 * 512
+    assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0))
+    H.assert_state_equal(ob, H.download(ctx), 1)
+    opath = str(tmp_path / "oracle.txt")
+    o.write_log(opath, syn.milestone_groups)
+    assert open(opath).read() == open(path).read()
+
+
+def test_drain_begin_end_contract(cuda_device):
+    """C ABI: one drain in flight; end() returns what had been appended when begin() was queued, not later records;
+    a small max_records leaves the rest waiting."""
+    syn = S.ballistic_toy(speed=5.0, dt=0.01)
+    integ = H.make_mmvt_integrator(syn, "")
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    ctx.setPositions(syn.positions)
+    ctx.setVelocities(syn.velocities)
+    h, stream = integ._handle, ctx.stream_ptr
+    buf = (L.Record * 4096)()
+    n, waiting = C.c_int64(0), C.c_int64(0)
+    assert L.lib.seekr2_b200_drain_end(h, buf, 4096, C.byref(n), None) == L.ERR_INVALID          # nothing in flight
+    integ.drainInterval = 1 << 30
+    integ._update_params(); ctx.prepareForces(); integ._first_step_check(); integ._before_first_step()
+    integ._issue(200)
+    assert L.lib.seekr2_b200_drain_begin(h, 4096, stream) == L.OK
+    assert L.lib.seekr2_b200_drain_begin(h, 4096, stream) == L.ERR_INVALID                         # one at a time
+    integ._issue(200)                                                                              # queued BEHIND the drain
+    assert L.lib.seekr2_b200_drain_end(h, buf, 4096, C.byref(n), C.byref(waiting)) == L.OK
+    first = n.value
+    assert first > 10 and waiting.value == 0 and max(buf[i].step for i in range(first)) < 200
+    assert L.lib.seekr2_b200_drain_begin(h, 5, stream) == L.OK                                     # small window
+    assert L.lib.seekr2_b200_drain_end(h, buf, 5, C.byref(n), C.byref(waiting)) == L.OK
+    assert n.value == 5 and waiting.value > 0 and min(buf[i].step for i in range(5)) >= 200
+    left = waiting.value
+    assert L.lib.seekr2_b200_drain(h, buf, 4096, C.byref(n), stream) == L.OK and n.value == left
+    assert integ.getAnchorState(0).ring_head == first + 5 + left
