@@ -208,6 +208,12 @@ def main() -> None:
         syn, positions, forces, shells = build_workload(A, args.atoms, seed + 1000 * rank)
         if kind == "mmvt":
             integ = H.make_mmvt_integrator(syn, "")
+        elif kind == "mmvt_middle":
+            integ = H.make_mmvt_integrator(syn, "", middle=True)
+        elif kind in ("elber", "elber_middle"):
+            integ = (s2.ElberLangevinMiddleIntegrator if kind == "elber_middle" else s2.ElberLangevinIntegrator)(300.0, 1.0, DT_PS, "")
+            integ.addSrcMilestoneGroup(1)              # the shell boundaries' force group: crossings reset the clock
+            integ.setEndOnSrcMilestone(False)
         else:
             integ = s2.LangevinIntegrator(300.0, 1.0, DT_PS)
         integ.setRandomNumberSeed(seed + rank)
@@ -308,6 +314,15 @@ def main() -> None:
     mmvt_over_langevin = (kernel_ms / launches) / (l_kernel / l_launches)
     del ctx_l, integ_l
 
+    # ---- the other integrators of the plugin on the same buffers (BASELINE.json configs[2]) --
+    variants = {"mmvt": kernel_ms / launches * 1e3, "langevin": l_kernel / l_launches * 1e3}
+    v_steps = max(STEPS_PER_GRAPH, min(args.steps, 512) // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
+    for kind in ("mmvt_middle", "elber", "elber_middle"):
+        ctx_v, integ_v, _ = make_context(kind)
+        _, kv, nv, _ = timed_run(ctx_v, integ_v, v_steps, W)
+        variants[kind] = kv / nv * 1e3
+        del ctx_v, integ_v
+
     # ---- latency mode: ONE anchor per GPU (the literal "8 anchors one per GPU" configuration) ------
     A_saved, A = A, 1
     ctx1, integ1, _ = make_context("mmvt")
@@ -384,6 +399,44 @@ def main() -> None:
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": e_dt / e_steps * 1e3,
                "note": "integrator.step(1) per step: H2D of the force buffer from pinned host memory, one fused launch, the step's crossing records drained to pinned host memory and appended to the integrator's record list; PCIe-bound by the force upload"}
 
+    # ---- the call a user of the reference makes: context.setPositions / setVelocities, integrator.step(n) with a
+    #      device-side force pass every step (harness tether kernel standing in for OpenMM's), context.getState ----
+    api_call = None
+    if not args.no_e2e:
+        del ctx, integ
+        syn_t, positions_t, _, _ = build_workload(A, args.atoms, seed + 1000 * rank)
+        syn_t.system.addForce(s2.TetherForce(1000.0))
+        integ_t = H.make_mmvt_integrator(syn_t, "")
+        integ_t.setRandomNumberSeed(seed + 9 + rank)
+        integ_t.ringCapacity = 1 << 14
+        integ_t.setUseGraph(True, STEPS_PER_GRAPH)
+        ctx_t = s2.Context(syn_t.system, integ_t, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=A)
+        n_call = max(STEPS_PER_GRAPH, min(args.steps, 1024) // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
+
+        def call():
+            ctx_t.setPositions(positions_t)
+            ctx_t.setVelocities(syn_t.velocities)
+            integ_t.step(n_call)
+            return ctx_t.getState(getPositions=True, getVelocities=True)
+
+        call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        state = call()
+        c_dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([c_dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c_dt = float(t.item())
+        api_call = {"value": ns_per_day(n_call / c_dt) * A * world, "unit": "anchor-ns/day", "steps_per_call": n_call,
+                    "seconds_per_call": c_dt, "h2d_bytes_per_call": A * ctx_t.padded_num_atoms * (16 + 16 + 32),
+                    "d2h_bytes_per_call": A * args.atoms * 48,
+                    "note": "setPositions + setVelocities (H2D) + integrator.step(n) with a tether-force kernel before every step "
+                            "(2 launches per step, CUDA graph) + getState(positions, velocities) (D2H), wall clock"}
+        del ctx_t, integ_t, state
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(1, args.cpu_steps or 32000, 16, args.atoms, seed)   # ~12 s at ~0.38 ms per anchor-step
@@ -394,7 +447,8 @@ def main() -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "ns_per_day_per_anchor": value / (A * world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches + fills, "roofline": roofline, "cpu_baseline": cpu,
-                "mmvt_over_plain_langevin": mmvt_over_langevin, "single_anchor_per_gpu": single_anchor, "box_100k": box,
+                "mmvt_over_plain_langevin": mmvt_over_langevin, "us_per_launch_by_integrator": variants,
+                "single_anchor_per_gpu": single_anchor, "box_100k": box, "api_call": api_call,
                 "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
                 "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
         emit(line)
