@@ -335,6 +335,18 @@ def main() -> None:
                      "plain_langevin_us_per_step": t1l * 1e3 / args.steps, "mmvt_over_plain_langevin": t1 / t1l,
                      "note": "1 anchor per GPU, L2-resident, launch-latency bound (the CV -> decision -> store chain is "
                              "serial inside the launch); CUDA graph of 32 steps"}
+    # launch overhead per step: the same graphs on a 64-atom system (nothing to stream: what is left is the launch
+    # itself and, for MMVT, the serial gather -> centroid -> decision -> store chain inside it)
+    atoms_saved, args.atoms = args.atoms, 64
+    ctx1, integ1, _ = make_context("mmvt")
+    t0m, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    del ctx1, integ1
+    ctx1, integ1, _ = make_context("langevin")
+    t0l, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    del ctx1, integ1
+    args.atoms = atoms_saved
+    single_anchor["launch_overhead_us_per_step"] = {"mmvt": t0m * 1e3 / args.steps, "plain_langevin": t0l * 1e3 / args.steps,
+                                                    "note": "1 anchor x 64 atoms, CUDA graph of 32 steps"}
     A = A_saved
 
     # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---
