@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libseekr2_b200.so")
+LIB_PATH = os.environ.get("SEEKR2_B200_LIBRARY") or os.path.join(_HERE, "libseekr2_b200.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
 ABI_VERSION = 6

@@ -68,21 +68,22 @@ __device__ __forceinline__ void cv_clear(CvShared& sh, int num_groups) {
     if (threadIdx.x < num_groups * 3) sh.acc[threadIdx.x] = 0;
 }
 
-// sum over the 32 lanes of a converged warp, modulo 2^64 (exact whenever the true sum fits in int64)
+// sum over the 32 lanes of a converged warp, modulo 2^64 (exact whenever the true sum fits in int64): three limbs
+// of 21 / 21 / 22 (signed) bits, each limb sum fits in 27 bits -> three independent REDUX.SUM
 __device__ __forceinline__ long long warp_sum_s64(long long q) {
-    const unsigned long long u = (unsigned long long) q;
-    const unsigned s0 = __reduce_add_sync(kFullWarp, (unsigned) (u & 0xFFFFu));
-    const unsigned s1 = __reduce_add_sync(kFullWarp, (unsigned) ((u >> 16) & 0xFFFFu));
-    const unsigned s2 = __reduce_add_sync(kFullWarp, (unsigned) ((u >> 32) & 0xFFFFu));
-    const int s3 = __reduce_add_sync(kFullWarp, (int) (q >> 48));                    // signed top limb
-    return (long long) (((unsigned long long) (long long) s3 << 48) + ((unsigned long long) s2 << 32) +
-                        ((unsigned long long) s1 << 16) + (unsigned long long) s0);
+    const unsigned s0 = __reduce_add_sync(kFullWarp, (unsigned) ((unsigned long long) q & 0x1FFFFFu));
+    const unsigned s1 = __reduce_add_sync(kFullWarp, (unsigned) (((unsigned long long) q >> 21) & 0x1FFFFFu));
+    const int s2 = __reduce_add_sync(kFullWarp, (int) (q >> 42));                   // signed top limb
+    return (long long) (((unsigned long long) (long long) s2 << 42) + ((unsigned long long) s1 << 21) + (unsigned long long) s0);
 }
 
 // Adds one slot's weighted position to its group's fixed-point accumulator.  Must be called by all
-// 32 lanes of a warp (invalid lanes pass valid=false).  Slots are sorted by group, so a warp almost
-// always covers a single group: then the three sums are shuffle-reduced and committed with one
-// shared-memory atomic per component; otherwise every lane commits its own.
+// 32 lanes of a warp (invalid lanes pass valid=false).  The host pads every group to a multiple of 32 slots, so
+// a warp covers a single group: the three sums are REDUX-reduced and committed by lane 0 -- with a plain store
+// when the whole group lives in this one warp (g carries kGroupSingleWarp: the common case, no CAS loop and no
+// need for a cleared accumulator), with one shared-memory atomic per component otherwise.  A warp that does mix
+// groups falls back to per-lane atomics.
+constexpr int kGroupSingleWarp = 0x4000;
 __device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, double w, double px,
                                               double py, double pz) {
     long long qx = 0, qy = 0, qz = 0;
@@ -95,19 +96,23 @@ __device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, d
     if (vmask == 0) return;
     const int gref = __shfl_sync(kFullWarp, g, __ffs(vmask) - 1);
     const bool uniform = __all_sync(kFullWarp, !valid || g == gref);
+    const int gi = gref & (kGroupSingleWarp - 1);
     if (uniform) {
-        // exact 64-bit warp sums from four 16-bit limbs each: every limb sum fits in 21 bits, so the
-        // twelve REDUX.SUM are independent single instructions (no 5-level shuffle chain)
         qx = warp_sum_s64(qx); qy = warp_sum_s64(qy); qz = warp_sum_s64(qz);
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 0], (unsigned long long) qx);
-            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 1], (unsigned long long) qy);
-            atomicAdd((unsigned long long*) &sh.acc[gref * 3 + 2], (unsigned long long) qz);
+            if (gref & kGroupSingleWarp) {
+                sh.acc[gi * 3 + 0] = qx; sh.acc[gi * 3 + 1] = qy; sh.acc[gi * 3 + 2] = qz;
+            } else {
+                atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 0], (unsigned long long) qx);
+                atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 1], (unsigned long long) qy);
+                atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 2], (unsigned long long) qz);
+            }
         }
     } else if (valid) {
-        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 0], (unsigned long long) qx);
-        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 1], (unsigned long long) qy);
-        atomicAdd((unsigned long long*) &sh.acc[g * 3 + 2], (unsigned long long) qz);
+        const int gl = g & (kGroupSingleWarp - 1);
+        atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 0], (unsigned long long) qx);
+        atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 1], (unsigned long long) qy);
+        atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 2], (unsigned long long) qz);
     }
 }
 
@@ -122,40 +127,53 @@ __device__ __forceinline__ double cv_sqdist(const CvShared& sh, int ga, int gb) 
     return __fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0)));
 }
 
-// one boundary term; evaluated by lane b of warp 0 after the accumulators are complete
+// the two rarer forms of the examples (demo4 pair-sum, demo5 angle): kept out of line so that the common path
+// below stays short, straight-line code (it is executed once per launch by a single warp, on the critical path
+// of the decision hand-off)
+__device__ __noinline__ double cv_term_rare(const long long* acc, const Boundary* bp) {
+    const Boundary& b = *bp;
+    auto cen = [&](int g, int c) { return __dmul_rn(__ll2double_rn(acc[g * 3 + c]), kFixedInvScale); };
+    auto sqdist = [&](int ga, int gb) {
+        const double d0 = __dsub_rn(cen(ga, 0), cen(gb, 0)), d1 = __dsub_rn(cen(ga, 1), cen(gb, 1)), d2 = __dsub_rn(cen(ga, 2), cen(gb, 2));
+        return __fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0)));
+    };
+    if (b.type == SEEKR2_B200_CV_PAIR_SUM) {
+        double sum = sqdist(b.groups[0], b.groups[1]);
+        for (int p = 1; p < b.axis; p++) sum = __dadd_rn(sum, sqdist(b.groups[2 * p], b.groups[2 * p + 1]));
+        return __dsub_rn(sum, __dmul_rn(b.threshold, b.threshold));
+    }
+    double a[3], v[3];                                   // SEEKR2_B200_CV_ANGLE
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double mid = cen(b.groups[1], c);
+        a[c] = __dsub_rn(cen(b.groups[0], c), mid);
+        v[c] = __dsub_rn(cen(b.groups[2], c), mid);
+    }
+    const double dot = __fma_rn(a[2], v[2], __fma_rn(a[1], v[1], __dmul_rn(a[0], v[0])));
+    const double na2 = __fma_rn(a[2], a[2], __fma_rn(a[1], a[1], __dmul_rn(a[0], a[0])));
+    const double nb2 = __fma_rn(v[2], v[2], __fma_rn(v[1], v[1], __dmul_rn(v[0], v[0])));
+    return __dsub_rn(__dmul_rn(b.center[0], __dsqrt_rn(__dmul_rn(na2, nb2))), dot);   // center[0] = cos(ref)
+}
+
+// one boundary term; evaluated by lane b of warp 0 after the accumulators are complete.  Sphere (pair or fixed
+// centre) and plane -- what MMVT anchors are made of -- are computed without a branch and selected.
 __device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b) {
     double u;
-    if (b.type == SEEKR2_B200_CV_PLANE) {
-        u = __dsub_rn(cv_centroid(sh, b.groups[0], b.axis), b.threshold);
-    } else if (b.type == SEEKR2_B200_CV_PAIR_SUM) {
-        double sum = cv_sqdist(sh, b.groups[0], b.groups[1]);
-        for (int p = 1; p < b.axis; p++) sum = __dadd_rn(sum, cv_sqdist(sh, b.groups[2 * p], b.groups[2 * p + 1]));
-        u = __dsub_rn(sum, __dmul_rn(b.threshold, b.threshold));
-    } else if (b.type == SEEKR2_B200_CV_ANGLE) {
-        double a[3], v[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const double mid = cv_centroid(sh, b.groups[1], c);
-            a[c] = __dsub_rn(cv_centroid(sh, b.groups[0], c), mid);
-            v[c] = __dsub_rn(cv_centroid(sh, b.groups[2], c), mid);
-        }
-        const double dot = __fma_rn(a[2], v[2], __fma_rn(a[1], v[1], __dmul_rn(a[0], v[0])));
-        const double na2 = __fma_rn(a[2], a[2], __fma_rn(a[1], a[1], __dmul_rn(a[0], a[0])));
-        const double nb2 = __fma_rn(v[2], v[2], __fma_rn(v[1], v[1], __dmul_rn(v[0], v[0])));
-        u = __dsub_rn(__dmul_rn(b.center[0], __dsqrt_rn(__dmul_rn(na2, nb2))), dot);   // center[0] = cos(ref)
+    if (b.type > SEEKR2_B200_CV_PLANE) {
+        u = cv_term_rare(sh.acc, &b);
     } else {
-        double dx, dy, dz;
-        if (b.type == SEEKR2_B200_CV_SPHERE_PAIR) {
-            dx = __dsub_rn(cv_centroid(sh, b.groups[0], 0), cv_centroid(sh, b.groups[1], 0));
-            dy = __dsub_rn(cv_centroid(sh, b.groups[0], 1), cv_centroid(sh, b.groups[1], 1));
-            dz = __dsub_rn(cv_centroid(sh, b.groups[0], 2), cv_centroid(sh, b.groups[1], 2));
-        } else {
-            dx = __dsub_rn(cv_centroid(sh, b.groups[0], 0), b.center[0]);
-            dy = __dsub_rn(cv_centroid(sh, b.groups[0], 1), b.center[1]);
-            dz = __dsub_rn(cv_centroid(sh, b.groups[0], 2), b.center[2]);
-        }
+        const int ga = b.groups[0], gb = b.groups[1];     // groups[1] is a valid index (0) when unused
+        const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
+        const double ax = cv_centroid(sh, ga, 0), ay = cv_centroid(sh, ga, 1), az = cv_centroid(sh, ga, 2);
+        const double bx = pair ? cv_centroid(sh, gb, 0) : b.center[0];
+        const double by = pair ? cv_centroid(sh, gb, 1) : b.center[1];
+        const double bz = pair ? cv_centroid(sh, gb, 2) : b.center[2];
+        const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
         const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
-        u = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
+        const double u_sphere = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
+        const double along = b.axis == 0 ? ax : (b.axis == 1 ? ay : az);
+        const double u_plane = __dsub_rn(along, b.threshold);
+        u = b.type == SEEKR2_B200_CV_PLANE ? u_plane : u_sphere;
     }
     const double ku = __dmul_rn(b.k, u);
     if (b.style == SEEKR2_B200_STYLE_RAW) return ku;

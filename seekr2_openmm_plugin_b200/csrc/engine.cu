@@ -282,11 +282,16 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             slot_group.push_back(g);
             slot_weight.push_back(cfg->group_weights[j] / sum);
         }
+        const size_t first = slot_atom.size() - (size_t) (hi - lo);
         while (slot_atom.size() % 32 != 0) {
             slot_atom.push_back(cfg->group_atoms[hi - 1]);
             slot_group.push_back(g);
             slot_weight.push_back(0.0);
         }
+        // a group that fits into one warp's 32 slots is summed by that warp alone: its leader stores the sums
+        // instead of adding them atomically (cv_accumulate)
+        if (slot_atom.size() - first == 32)
+            for (size_t j = first; j < slot_atom.size(); j++) slot_group[j] |= kGroupSingleWarp;
     }
     const int num_slots = (int) slot_atom.size();
     for (int a = 0; a < cfg->num_anchors; a++)
