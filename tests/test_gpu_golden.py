@@ -45,3 +45,53 @@ def test_gpu_reproduces_golden(cuda_device, tmp_path, name, mode):
     assert list(st.N_alpha_beta[:4]) == want["N_alpha_beta"] and list(st.Ri_alpha[:4]) == want["Ri_alpha"]
     assert len(integ.getRecords(0)) == want["records"]
     assert filecmp.cmp(path, os.path.join(GOLDEN, name + ".csv"), shallow=False)
+
+
+# ---- golden vectors written by the REFERENCE'S OWN CUDA platform (tests/golden/ref_cuda_platform/) -------------------
+
+import numpy as np  # noqa: E402
+
+import ref_platform_cases as RC  # noqa: E402
+from shim_io import PRECISIONS  # noqa: E402
+
+REF_GOLDEN = os.path.join(GOLDEN, "ref_cuda_platform")
+spec2 = importlib.util.spec_from_file_location("make_ref_platform_golden", os.path.join(GOLDEN, "make_ref_platform_golden.py"))
+G2 = importlib.util.module_from_spec(spec2)
+spec2.loader.exec_module(G2)
+REF_MANIFEST = json.load(open(os.path.join(REF_GOLDEN, "manifest.json")))
+
+
+@pytest.mark.parametrize("name", sorted(RC.cases()))
+@pytest.mark.parametrize("mode", ["fused_graph", "two_pass"])
+def test_gpu_reproduces_reference_cuda_platform_outputs(cuda_device, tmp_path, name, mode):
+    """The harness path (public integrator API -> C ABI -> fused / two-pass kernels) writes the very bytes the reference's
+    own CUDA platform wrote for the same seeded inputs: crossings file, statistics file, final buffers."""
+    case = RC.cases()[name]
+    want = REF_MANIFEST[name]
+    syn = case["make"]()
+    n = syn.positions.shape[0]
+    integ = RC.make_integrator(case, syn)
+    path, spath = str(tmp_path / "gpu.csv"), str(tmp_path / "gpu.stats")
+    integ.setOutputFileName(path)
+    if want.get("has_stats"):
+        integ.setSaveStatisticsFileName(spath)
+    precision = PRECISIONS[case["precision"]]
+    hb = H.make_host_buffers(precision, syn.positions, syn.velocities, syn.masses)
+    pool = RC.pool_for(case, syn)
+    steps = sum(case["steps"])
+    if pool is None:
+        pool = np.zeros((steps * hb.posq.shape[0], 4), dtype=np.float32)
+    integ.setStepMode("fused" if mode == "fused_graph" else "two_pass")
+    if mode == "fused_graph":
+        integ.setUseGraph(True, 4)
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": case["precision"]})
+    H.upload(ctx, [hb])
+    ctx.setRandomPool(pool)
+    for chunk in case["steps"]:
+        integ.step(chunk)
+    assert open(path, "rb").read() == open(os.path.join(REF_GOLDEN, name + ".csv"), "rb").read()
+    assert G2.state_digest(H.download(ctx), n) == want["state_sha256"]
+    st = integ.getAnchorState(0)
+    assert (st.time, st.step_count) == (want["time"], want["step_count"])
+    if want.get("has_stats"):
+        assert open(spath, "rb").read() == open(os.path.join(REF_GOLDEN, name + ".stats"), "rb").read()
