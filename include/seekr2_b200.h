@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 6
+#define SEEKR2_B200_ABI_VERSION 7
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -78,9 +78,16 @@ enum {
 
 /* flags */
 enum {
-    SEEKR2_B200_FLAG_RESTORE_CORRECTION = 1  /* on a bounce also restore posqCorrection.  The
+    SEEKR2_B200_FLAG_RESTORE_CORRECTION = 1, /* on a bounce also restore posqCorrection.  The
                                                 reference leaves the new correction in place
                                                 (langevin.cu:167-179); default 0 is bit-faithful   */
+    /* How the fused step (seekr2_b200_step) gets the crossing decision to the threads that store the
+       atoms.  Results are bit-identical either way; default (neither flag) picks by launch size:
+       LOCAL when the whole launch is resident at once (one or a few anchors per GPU, latency-bound),
+       HANDOFF for batched, bandwidth-bound launches.                                                 */
+    SEEKR2_B200_FLAG_DECIDE_LOCAL = 2,       /* every block evaluates the boundaries itself (needs
+                                                save_state_slots == 0 and <= 256 padded group slots)  */
+    SEEKR2_B200_FLAG_DECIDE_HANDOFF = 4      /* one decide block per anchor publishes the decision    */
 };
 
 /* integrator kind */
@@ -236,6 +243,9 @@ int seekr2_b200_create(const seekr2_b200_config* config, seekr2_b200_handle* out
 int seekr2_b200_destroy(seekr2_b200_handle h);
 const char* seekr2_b200_last_error(void);
 int seekr2_b200_abi_version(void);
+
+/* 1 if the fused step of this engine runs in LOCAL decision mode, 0 for the decide-block hand-off   */
+int seekr2_b200_decision_mode(seekr2_b200_handle h);
 
 /* ---- parameters ---------------------------------------------------------------------------- */
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SEEKR2_B200_LIBRARY") or os.path.join(_HERE, "libseekr2_b200.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -24,6 +24,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_FIRST_STEP, ERR_RING_OVERFLOW, ERR_IO, ERR_NO_FOR
 SINGLE, MIXED, DOUBLE = 0, 1, 2
 VARIANT_CUDA, VARIANT_REFERENCE = 0, 1
 FLAG_RESTORE_CORRECTION = 1
+FLAG_DECIDE_LOCAL = 2
+FLAG_DECIDE_HANDOFF = 4
 KIND_LANGEVIN, KIND_MMVT, KIND_ELBER = 0, 1, 2
 SCHEME_LANGEVIN, SCHEME_MIDDLE = 0, 1
 CV_SPHERE_PAIR, CV_SPHERE_FIXED, CV_PLANE, CV_PAIR_SUM, CV_ANGLE = 0, 1, 2, 3, 4
@@ -101,6 +103,7 @@ SYMBOLS = {
     "seekr2_b200_destroy": (C.c_int, [_P]),
     "seekr2_b200_last_error": (C.c_char_p, []),
     "seekr2_b200_abi_version": (C.c_int, []),
+    "seekr2_b200_decision_mode": (C.c_int, [C.c_void_p]),
     "seekr2_b200_set_params": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "seekr2_b200_get_params": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "seekr2_b200_sync_groups": (C.c_int, [_P, C.POINTER(Buffers), _P]),

@@ -50,6 +50,8 @@ struct EngineDev {
     int prefetch_ahead;          // first-wave blocks prefetch the tile of block (own + this) into L2 while they wait (0 = off)
     int* flags;                  // [2][A] decision hand-off of the fused kernel: 0 = not yet; bit0 valid, bit1 bounce,
                                  // bit2 save the advanced state into snapshot slot (flag >> 4)
+    int mmvt_any_term;           // 1: every force-group-1 term is STEP style with a bitcode in [1, 2^31], so the MMVT value
+                                 // is positive exactly when one of them is active (LOCAL mode skips the in-order sum)
     int snap_slots;              // save_state_slots (0 = off)
     void* snap_posq;             // real4 [A][slots][Np]   pre-bounce positions of the last crossings
     void* snap_corr;             // real4 [A][slots][Np]   (MIXED only)
@@ -113,6 +115,25 @@ __device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, d
         atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 0], (unsigned long long) qx);
         atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 1], (unsigned long long) qy);
         atomicAdd((unsigned long long*) &sh.acc[gl * 3 + 2], (unsigned long long) qz);
+    }
+}
+
+// cv_accumulate() for callers that know the host's slot layout holds (every group padded to whole warps, so the 32 lanes
+// of a warp always belong to one group): no votes, straight to the REDUX sums
+__device__ __forceinline__ void cv_accumulate_aligned(CvShared& sh, int g, double w, double px, double py, double pz) {
+    long long qx = __double2ll_rn(__dmul_rn(__dmul_rn(w, px), kFixedScale));
+    long long qy = __double2ll_rn(__dmul_rn(__dmul_rn(w, py), kFixedScale));
+    long long qz = __double2ll_rn(__dmul_rn(__dmul_rn(w, pz), kFixedScale));
+    qx = warp_sum_s64(qx); qy = warp_sum_s64(qy); qz = warp_sum_s64(qz);
+    if ((threadIdx.x & 31) == 0) {
+        const int gi = g & (kGroupSingleWarp - 1);
+        if (g & kGroupSingleWarp) {
+            sh.acc[gi * 3 + 0] = qx; sh.acc[gi * 3 + 1] = qy; sh.acc[gi * 3 + 2] = qz;
+        } else {
+            atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 0], (unsigned long long) qx);
+            atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 1], (unsigned long long) qy);
+            atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 2], (unsigned long long) qz);
+        }
     }
 }
 
@@ -180,9 +201,33 @@ __device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b)
     return ku >= 0.0 ? b.bitcode : 0.0;
 }
 
+// cv_term() for a boundary held in REGISTERS (b is a by-value copy whose fields are only accessed with static indices;
+// the rare forms index groups[] dynamically and therefore go through b_mem, the same boundary in memory)
+__device__ __forceinline__ double cv_term_regs(const CvShared& sh, const Boundary& b, const Boundary* b_mem) {
+    double u;
+    if (b.type > SEEKR2_B200_CV_PLANE) {
+        u = cv_term_rare(sh.acc, b_mem);
+    } else {
+        const int ga = b.groups[0], gb = b.groups[1];
+        const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
+        const double ax = cv_centroid(sh, ga, 0), ay = cv_centroid(sh, ga, 1), az = cv_centroid(sh, ga, 2);
+        const double bx = pair ? cv_centroid(sh, gb, 0) : b.center[0];
+        const double by = pair ? cv_centroid(sh, gb, 1) : b.center[1];
+        const double bz = pair ? cv_centroid(sh, gb, 2) : b.center[2];
+        const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+        const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+        const double u_sphere = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
+        const double along = b.axis == 0 ? ax : (b.axis == 1 ? ay : az);
+        const double u_plane = __dsub_rn(along, b.threshold);
+        u = b.type == SEEKR2_B200_CV_PLANE ? u_plane : u_sphere;
+    }
+    const double ku = __dmul_rn(b.k, u);
+    if (b.style == SEEKR2_B200_STYLE_RAW) return ku;
+    return ku >= 0.0 ? b.bitcode : 0.0;
+}
+
 // warp 0: lane b evaluates boundary b of this anchor into shared memory
-__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, const Boundary& b) {
-    const int lane = threadIdx.x;
+__device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, const Boundary& b, int lane = threadIdx.x) {
     if (lane < e.num_boundaries) {
         sh.term[lane] = cv_term(sh, b);
         sh.force_group[lane] = b.force_group;

@@ -45,6 +45,7 @@ int fail(int code, const char* fmt, ...) {
 
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
+constexpr int kLocalBlocksPerSm = 2;           // LOCAL decision mode when the streaming blocks number at most SMs x this (auto mode)
 constexpr long long kStageRecords = 1 << 16;   // staging buffer of the asynchronous drain (2.6 MB of mapped pinned memory)
 constexpr double kBoltzmann = 1.380649e-23;
 constexpr double kAvogadro = 6.02214076e23;
@@ -69,6 +70,7 @@ struct seekr2_b200_engine {
     bool params_set = false;
     int parity = 0;                 // slab half holding the current group state
     bool slab_valid = false;
+    bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
     // device allocations
     int* d_slot_atom = nullptr;
     int* d_slot_group = nullptr;
@@ -158,6 +160,13 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
 
 template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
     const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
+    if (h->local_decide) {
+        // kThreads streaming threads + one thread per (warp-padded) boundary-group slot
+        const unsigned threads = kThreads + (KIND == SEEKR2_B200_KIND_LANGEVIN ? 0u : (unsigned) ((h->dev.num_slots > 0 ? h->dev.num_slots + 31 : 32) & ~31));
+        fused_local_kernel<P, KIND, SCHEME><<<dim3((unsigned) bpa, (unsigned) h->cfg.num_anchors, 1), threads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity);
+        CUDA_TRY(cudaGetLastError());
+        return SEEKR2_B200_OK;
+    }
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
     fused_step_kernel<P, KIND, SCHEME><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa);
     CUDA_TRY(cudaGetLastError());
@@ -367,6 +376,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         CREATE_TRY(cudaMalloc(&h->d_boundaries, sizeof(Boundary) * nb));
         CREATE_TRY(cudaMemcpy(h->d_boundaries, bounds.data(), sizeof(Boundary) * nb, cudaMemcpyHostToDevice));
     }
+    d.mmvt_any_term = 1;
+    for (size_t i = 0; i < (size_t) A * cfg->num_boundaries; i++) {
+        const Boundary& bd = cfg->boundaries[i];
+        if (bd.force_group == 1 && !(bd.style == SEEKR2_B200_STYLE_STEP && bd.bitcode >= 1.0 && bd.bitcode <= 2147483648.0)) d.mmvt_any_term = 0;
+    }
     CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
     CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * A));
@@ -418,6 +432,22 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         d.head_start_target = A * slot_warps;
         d.prefetch_ahead = d.first_wave_blocks;
         if (const char* pf = getenv("SEEKR2_B200_PREFETCH")) if (pf[0] == '0') d.prefetch_ahead = 0;               // tuning knob
+        // Decision mode of the fused step.  LOCAL (every block evaluates the boundaries itself, no hand-off) is for the
+        // latency-bound regime: the whole launch resident at once with room to spare; the decide-block hand-off is for
+        // batched, HBM-bound launches, where redundant group gathers and 2x the registers would cost bandwidth.
+        const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
+        const bool eligible = d.snap_slots == 0 && num_slots <= kThreads;
+        bool local = eligible && stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
+        if (const char* m = getenv("SEEKR2_B200_DECIDE")) {                                                         // A/B knob
+            if (m[0] == 'l') local = eligible;
+            if (m[0] == 'h') local = false;
+        }
+        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_HANDOFF) local = false;
+        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_LOCAL) {
+            if (!eligible) return bail(fail(SEEKR2_B200_ERR_INVALID, "FLAG_DECIDE_LOCAL needs save_state_slots == 0 and at most %d group slots (have %d)", kThreads, num_slots));
+            local = true;
+        }
+        h->local_decide = local;
     }
     *out = h;
     return SEEKR2_B200_OK;
@@ -451,6 +481,8 @@ int seekr2_b200_debug_set_probe(seekr2_b200_handle h, void* d_probe) {
     h->dev.probe = (long long*) d_probe;
     return SEEKR2_B200_OK;
 }
+
+int seekr2_b200_decision_mode(seekr2_b200_handle h) { return h && h->local_decide ? 1 : 0; }
 
 int seekr2_b200_get_params(seekr2_b200_handle h, double out[3]) {
     if (!h || !out) return fail(SEEKR2_B200_ERR_INVALID, "null argument");

@@ -83,6 +83,17 @@ class _B200LangevinBase:
     def setRestoreCorrection(self, on: bool) -> None:
         self.flags = (self.flags | L.FLAG_RESTORE_CORRECTION) if on else (self.flags & ~L.FLAG_RESTORE_CORRECTION)
 
+    def setDecisionMode(self, mode: str) -> None:
+        """How the fused step hands the crossing decision to the storing threads: "auto" (by launch size), "local"
+        (every block evaluates the boundaries; latency-bound launches) or "handoff" (one decide block per anchor).
+        Bit-identical results; takes effect when the Context is created."""
+        bits = {"auto": 0, "local": L.FLAG_DECIDE_LOCAL, "handoff": L.FLAG_DECIDE_HANDOFF}[mode]
+        self.flags = (self.flags & ~(L.FLAG_DECIDE_LOCAL | L.FLAG_DECIDE_HANDOFF)) | bits
+
+    def getDecisionMode(self) -> str:
+        """The mode the engine actually runs in (after the Context exists)."""
+        return "local" if L.lib.seekr2_b200_decision_mode(self._handle) else "handoff"
+
     def setStepMode(self, mode: str) -> None:
         assert mode in ("fused", "two_pass")
         self.stepMode = mode

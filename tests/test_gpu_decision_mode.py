@@ -1,0 +1,90 @@
+"""The two decision modes of the fused step (include/seekr2_b200.h FLAG_DECIDE_LOCAL / FLAG_DECIDE_HANDOFF) are the same
+function: LOCAL (every block advances the boundary-group atoms and evaluates the boundaries itself) and HANDOFF (one decide
+block per anchor publishes the decision) give bit-identical atoms, crossing records and statistics -- and both equal the CPU
+oracle (the other GPU test modules run in both modes through the `decision_mode` fixture)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import L, s2
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(syn, A, positions, mode, steps, graph, middle=False, kind="mmvt", pool=None, seed=11):
+    if kind == "mmvt":
+        integ = H.make_mmvt_integrator(syn, "", middle=middle)
+    else:
+        integ = (s2.ElberLangevinMiddleIntegrator if middle else s2.ElberLangevinIntegrator)(syn.temperature, syn.friction, syn.dt, "")
+        integ.addSrcMilestoneGroup(1)
+        integ.setEndOnSrcMilestone(False)
+    integ.setDecisionMode(mode)
+    integ.setRandomNumberSeed(seed)
+    if graph:
+        integ.setUseGraph(True, graph)
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
+    assert integ.getDecisionMode() == mode
+    ctx.setPositions(positions)
+    ctx.setVelocities(syn.velocities)
+    if pool is not None:
+        ctx.setRandomPool(pool)
+    integ.step(steps)
+    recs = [H.records_as_tuples(integ.getRecords(a)) for a in range(A)]
+    stats = [H.stats_tuple(integ.getAnchorState(a), 2) for a in range(A)]
+    clock = [(integ.getAnchorState(a).time, integ.getAnchorState(a).step_count) for a in range(A)]
+    return [H.download(ctx, a) for a in range(A)], recs, stats, clock
+
+
+def _shell_workload(A, n_atoms, seed):
+    rec, lig = list(range(0, 11)), list(range(11, 20))
+    syn = H.pair_sphere_system(n_atoms, rec, lig, 0.10, 0.14, seed, tether_k=0.0)
+    positions = np.empty((A, n_atoms, 3))
+    base = syn.positions.copy()
+    for a in range(A):
+        rin, rout = 0.10 + 0.04 * a, 0.14 + 0.04 * a
+        syn.boundary_force.setAnchorBondParameters(a, 0, [1.0, -1.0, rin])
+        syn.boundary_force.setAnchorBondParameters(a, 1, [2.0, 1.0, rout])
+        syn.positions = base.copy()
+        H.place_pair_distance(syn, rec, lig, 0.5 * (rin + rout))
+        positions[a] = syn.positions
+    syn.positions = base
+    return syn, positions
+
+
+@pytest.mark.parametrize("kind,middle", [("mmvt", False), ("mmvt", True), ("elber", False), ("elber", True)])
+@pytest.mark.parametrize("graph", [0, 8])
+def test_local_and_handoff_modes_are_bit_identical(cuda_device, kind, middle, graph):
+    """4 batched anchors x 3 000 atoms (12 blocks per anchor), in-kernel Philox normals, 400 steps with bounces."""
+    A, n = 4, 3000
+    out = {}
+    for mode in ("local", "handoff"):
+        syn, positions = _shell_workload(A, n, H.SEED_BASE + 61)
+        out[mode] = _run(syn, A, positions, mode, 400, graph, middle=middle, kind=kind)
+    (gl, rl, sl, cl), (gh, rh, sh, ch) = out["local"], out["handoff"]
+    assert rl == rh and sl == sh and cl == ch
+    if kind == "mmvt":
+        assert sum(len(r) for r in rl) >= 4, "the run must bounce"
+    for a in range(A):
+        H.assert_state_equal(gl[a], gh[a], n, f"local vs handoff, anchor {a}")
+
+
+def test_auto_mode_picks_by_launch_size(cuda_device):
+    """Default: a launch that is resident at once runs LOCAL, a batched one the hand-off; save-state slots force the hand-off."""
+    syn, positions = _shell_workload(1, 3000, H.SEED_BASE + 62)
+    integ = H.make_mmvt_integrator(syn, "")
+    s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    assert integ.getDecisionMode() == "local"
+    syn, positions = _shell_workload(64, 3000, H.SEED_BASE + 62)
+    integ = H.make_mmvt_integrator(syn, "")
+    s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=64)
+    assert integ.getDecisionMode() == "handoff"
+    syn, positions = _shell_workload(1, 3000, H.SEED_BASE + 62)
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.setSaveStateFileName("/tmp/seekr2_b200_state")
+    s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    assert integ.getDecisionMode() == "handoff"
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.setSaveStateFileName("/tmp/seekr2_b200_state")
+    integ.setDecisionMode("local")
+    with pytest.raises(s2.Seekr2Error):
+        s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})

@@ -8,7 +8,7 @@ import pytest
 import helpers as H
 from helpers import L, s2
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("decision_mode")]
 
 
 @pytest.mark.parametrize("precision", ["single", "mixed", "double"])

@@ -10,7 +10,7 @@ import helpers as H
 import scenarios as S
 from helpers import L, s2
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("decision_mode")]
 NAMES = {L.SINGLE: "single", L.MIXED: "mixed", L.DOUBLE: "double"}
 
 

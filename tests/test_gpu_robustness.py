@@ -10,7 +10,7 @@ import helpers as H
 import scenarios as S
 from helpers import L, s2
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("decision_mode")]
 
 
 def test_set_positions_mid_run_resyncs_group_slab(cuda_device):

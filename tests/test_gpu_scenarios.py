@@ -9,7 +9,7 @@ import helpers as H
 import scenarios as S
 from helpers import L, s2
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("decision_mode")]
 
 
 def _same(o, ob, integ, gb, n, m):
