@@ -204,7 +204,7 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     A = args.anchors
 
-    def make_context(kind: str):
+    def make_context(kind: str, decision_mode: str = "auto"):
         syn, positions, forces, shells = build_workload(A, args.atoms, seed + 1000 * rank)
         if kind == "mmvt":
             integ = H.make_mmvt_integrator(syn, "")
@@ -217,6 +217,7 @@ def main() -> None:
         else:
             integ = s2.LangevinIntegrator(300.0, 1.0, DT_PS)
         integ.setRandomNumberSeed(seed + rank)
+        integ.setDecisionMode(decision_mode)
         integ.ringCapacity = 1 << 14
         integ.setUseGraph(True, STEPS_PER_GRAPH)
         ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=A,
@@ -304,7 +305,7 @@ def main() -> None:
     # still in L2 when the kernel ends); null otherwise
     traffic = 393.6e6 if (A, args.atoms) == (128, N_ATOMS) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
+                "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>" if integ.getDecisionMode() == "handoff" else "fused_local_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback"}
 
@@ -327,14 +328,20 @@ def main() -> None:
     A_saved, A = A, 1
     ctx1, integ1, _ = make_context("mmvt")
     t1, k1, n1, _ = timed_run(ctx1, integ1, args.steps, W)
+    mode1 = integ1.getDecisionMode()
     del ctx1, integ1
     ctx1, integ1, _ = make_context("langevin")
     t1l, k1l, n1l, _ = timed_run(ctx1, integ1, args.steps, W)
     del ctx1, integ1
+    ctx1, integ1, _ = make_context("mmvt", decision_mode="handoff")
+    t1h, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    del ctx1, integ1
     single_anchor = {"ns_per_day_per_anchor": ns_per_day(args.steps / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / args.steps,
                      "plain_langevin_us_per_step": t1l * 1e3 / args.steps, "mmvt_over_plain_langevin": t1 / t1l,
-                     "note": "1 anchor per GPU, L2-resident, launch-latency bound (the CV -> decision -> store chain is "
-                             "serial inside the launch); CUDA graph of 32 steps"}
+                     "decision_mode": mode1, "us_per_step_handoff_mode": t1h * 1e3 / args.steps,
+                     "note": "1 anchor per GPU, L2-resident, launch-latency bound; LOCAL decision mode (every block evaluates the "
+                             "boundaries in dedicated slot warps; the batched default workload above runs the decide-block hand-off); "
+                             "CUDA graph of 32 steps"}
     # launch overhead per step: the same graphs on a 64-atom system (nothing to stream: what is left is the launch
     # itself and, for MMVT, the serial gather -> centroid -> decision -> store chain inside it)
     atoms_saved, args.atoms = args.atoms, 64

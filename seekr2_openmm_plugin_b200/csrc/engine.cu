@@ -45,7 +45,8 @@ int fail(int code, const char* fmt, ...) {
 
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
-constexpr int kLocalBlocksPerSm = 2;           // LOCAL decision mode when the streaming blocks number at most SMs x this (auto mode)
+constexpr int kLocalBlocksPer2Sm = 5;          // auto mode: LOCAL decision when the streaming blocks number at most 2.5 x SMs (measured
+                                               // crossover on 23 036-atom anchors: LOCAL wins up to 4 anchors per GPU, the hand-off from 8)
 constexpr long long kStageRecords = 1 << 16;   // staging buffer of the asynchronous drain (2.6 MB of mapped pinned memory)
 constexpr double kBoltzmann = 1.380649e-23;
 constexpr double kAvogadro = 6.02214076e23;
@@ -70,6 +71,7 @@ struct seekr2_b200_engine {
     bool params_set = false;
     int parity = 0;                 // slab half holding the current group state
     bool slab_valid = false;
+    bool use_pdl = true;            // fused step kernels are launched with programmatic stream serialization (SEEKR2_B200_PDL=0: off)
     bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
     // device allocations
     int* d_slot_atom = nullptr;
@@ -163,13 +165,30 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
     if (h->local_decide) {
         // kThreads streaming threads + one thread per (warp-padded) boundary-group slot
         const unsigned threads = kThreads + (KIND == SEEKR2_B200_KIND_LANGEVIN ? 0u : (unsigned) ((h->dev.num_slots > 0 ? h->dev.num_slots + 31 : 32) & ~31));
-        fused_local_kernel<P, KIND, SCHEME><<<dim3((unsigned) bpa, (unsigned) h->cfg.num_anchors, 1), threads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity);
-        CUDA_TRY(cudaGetLastError());
+        // programmatic dependent launch: the next step's blocks may start their (static) prologue under this launch's body
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned) bpa, (unsigned) h->cfg.num_anchors, 1);
+        lc.blockDim = dim3(threads, 1, 1);
+        lc.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = h->use_pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity));
         return SEEKR2_B200_OK;
     }
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
-    fused_step_kernel<P, KIND, SCHEME><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa);
-    CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid, 1, 1);
+    lc.blockDim = dim3(kThreads, 1, 1);
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = h->use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa));
     return SEEKR2_B200_OK;
 }
 
@@ -437,7 +456,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         // batched, HBM-bound launches, where redundant group gathers and 2x the registers would cost bandwidth.
         const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
         const bool eligible = d.snap_slots == 0 && num_slots <= kThreads;
-        bool local = eligible && stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
+        bool local = eligible && 2 * stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPer2Sm;
         if (const char* m = getenv("SEEKR2_B200_DECIDE")) {                                                         // A/B knob
             if (m[0] == 'l') local = eligible;
             if (m[0] == 'h') local = false;
@@ -448,6 +467,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             local = true;
         }
         h->local_decide = local;
+        if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                   // A/B knob
     }
     *out = h;
     return SEEKR2_B200_OK;
