@@ -251,7 +251,7 @@ def main() -> None:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 if n == STEPS_PER_GRAPH:
-                    key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, integ._prev)
+                    key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, integ._prev, integ._steps_issued % 4)
                     if integ._graph_key != key:
                         raise RuntimeError("graph must be warm before the timed region")
                     L.check(L.lib.seekr2_b200_graph_launch(integ._handle, ctx.stream_ptr))
@@ -301,9 +301,9 @@ def main() -> None:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this very
-    # workload (profiles/r01b_fused_step_ncu_full.txt: 260.2 MB read + 133.4 MB written; the tail of the writes is
+    # workload (profiles/r01d_fused_step_ncu_full.txt: 260.2 MB read + 134.2 MB written; the tail of the writes is
     # still in L2 when the kernel ends); null otherwise
-    traffic = 393.6e6 if (A, args.atoms) == (128, N_ATOMS) else None
+    traffic = 394.4e6 if (A, args.atoms) == (128, N_ATOMS) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>" if integ.getDecisionMode() == "handoff" else "fused_local_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,

@@ -40,7 +40,8 @@ struct EngineDev {
     Record* ring;                // [A][ring_capacity]
     void* slab;                  // [2][A][num_slots] SlabEntry<P>
     int* decision;               // [A] bounce flag of the two-pass path
-    long long* step_shadow;      // [2][A] step index of the launch with that parity (stable during the launch)
+    long long* step_shadow;      // [4][A] step index of the fused launch with that phase (launch count mod 4): launch k reads
+                                 // phase k, writes phase k+2 -- stable during the launch and already final when launch k starts early (PDL)
     unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
     unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
     long long* probe;            // optional timing probe (debug, seekr2_b200_debug_set_probe)

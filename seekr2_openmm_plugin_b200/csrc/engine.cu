@@ -45,8 +45,8 @@ int fail(int code, const char* fmt, ...) {
 
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
-constexpr int kLocalBlocksPer2Sm = 5;          // auto mode: LOCAL decision when the streaming blocks number at most 2.5 x SMs (measured
-                                               // crossover on 23 036-atom anchors: LOCAL wins up to 4 anchors per GPU, the hand-off from 8)
+constexpr int kLocalBlocksPerSm = 4;           // auto mode: LOCAL decision when the streaming blocks number at most 4 x SMs (measured
+                                               // crossover on 23 036-atom anchors: LOCAL wins up to 6 anchors per GPU, the hand-off from 8)
 constexpr long long kStageRecords = 1 << 16;   // staging buffer of the asynchronous drain (2.6 MB of mapped pinned memory)
 constexpr double kBoltzmann = 1.380649e-23;
 constexpr double kAvogadro = 6.02214076e23;
@@ -69,7 +69,8 @@ struct seekr2_b200_engine {
     double params[3] = {0, 0, 0};   // vscale, fscale, noisescale
     double step_size = 0.0;
     bool params_set = false;
-    int parity = 0;                 // slab half holding the current group state
+    int phase = 0;                  // fused launches so far mod 4: bit 0 = slab half holding the current group state / flag half,
+                                    // the whole value = step_shadow slot the next launch reads
     bool slab_valid = false;
     bool use_pdl = true;            // fused step kernels are launched with programmatic stream serialization (SEEKR2_B200_PDL=0: off)
     bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
@@ -100,7 +101,7 @@ struct seekr2_b200_engine {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool capturing = false;
-    int capture_parity0 = 0;
+    int capture_phase0 = 0;
     int capture_steps = 0;
     int graph_steps = 0;
 };
@@ -153,7 +154,7 @@ int check_bufs(const seekr2_b200_engine* h, const seekr2_b200_buffers* b, bool n
 template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
     if (h->dev.num_slots > 0) {
         dim3 grid((unsigned) ((h->dev.num_slots + kThreads - 1) / kThreads), (unsigned) h->cfg.num_anchors, 1);
-        gather_groups_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->parity);
+        gather_groups_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->phase & 1);
     }
     decide_kernel<P, SEEKR2_B200_KIND_MMVT, 1><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
     CUDA_TRY(cudaGetLastError());
@@ -175,7 +176,7 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = attr;
         lc.numAttrs = h->use_pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity));
+        CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase));
         return SEEKR2_B200_OK;
     }
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
@@ -188,7 +189,7 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = h->use_pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->parity, bpa));
+    CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase, bpa));
     return SEEKR2_B200_OK;
 }
 
@@ -406,8 +407,12 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * A));
     CREATE_TRY(cudaMalloc(&h->d_flags, sizeof(int) * (2 * A + 2)));      // [2][A] flags + [2] head-start counters
     CREATE_TRY(cudaMemset(h->d_flags, 0, sizeof(int) * (2 * A + 2)));
-    CREATE_TRY(cudaMalloc(&h->d_step_shadow, sizeof(long long) * 2 * A));
-    CREATE_TRY(cudaMemset(h->d_step_shadow, 0, sizeof(long long) * 2 * A));
+    CREATE_TRY(cudaMalloc(&h->d_step_shadow, sizeof(long long) * 4 * A));
+    {   // launch 0 reads slot 0 (step 0), launch 1 slot 1 (step 1); slots 2 and 3 are written by launches 0 and 1
+        std::vector<long long> shadow(4 * (size_t) A, 0);
+        for (int a = 0; a < A; a++) shadow[(size_t) A + a] = 1;
+        CREATE_TRY(cudaMemcpy(h->d_step_shadow, shadow.data(), sizeof(long long) * 4 * A, cudaMemcpyHostToDevice));
+    }
     CREATE_TRY(cudaHostAlloc(&h->h_state, sizeof(AnchorState) * A, cudaHostAllocDefault));
     // initialize(): zero statistics, seed counters (CudaSeekr2Kernels.cpp:118-133,151-154,403-404)
     memset(h->h_state, 0, sizeof(AnchorState) * A);
@@ -456,7 +461,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         // batched, HBM-bound launches, where redundant group gathers and 2x the registers would cost bandwidth.
         const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
         const bool eligible = d.snap_slots == 0 && num_slots <= kThreads;
-        bool local = eligible && 2 * stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPer2Sm;
+        bool local = eligible && stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
         if (const char* m = getenv("SEEKR2_B200_DECIDE")) {                                                         // A/B knob
             if (m[0] == 'l') local = eligible;
             if (m[0] == 'h') local = false;
@@ -548,7 +553,7 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
                                 launch_fused_kind<MIXED>(h, bufs, random_index, s),
                                 launch_fused_kind<DOUBLE>(h, bufs, random_index, s));
     if (rc != SEEKR2_B200_OK) return rc;
-    h->parity ^= 1;   // slab half and decision flag alternate every launch
+    h->phase = (h->phase + 1) & 3;   // slab half and decision flag alternate every launch; the step-index slots cycle through four
     if (h->capturing) h->capture_steps++;
     return SEEKR2_B200_OK;
 }
@@ -594,7 +599,7 @@ int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
     if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
     CUDA_TRY(cudaStreamBeginCapture((cudaStream_t) stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    h->capture_parity0 = h->parity;
+    h->capture_phase0 = h->phase;
     h->capture_steps = 0;
     return SEEKR2_B200_OK;
 }
@@ -606,17 +611,17 @@ int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream) {
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamEndCapture((cudaStream_t) stream, &g));
     h->graph = g;
-    h->parity = h->capture_parity0;      // the captured steps have not run yet
+    h->phase = h->capture_phase0;        // the captured steps have not run yet
     h->graph_steps = h->capture_steps;
-    if (h->graph_steps & 1)
-        return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain an even number of fused steps (the slab parity is baked into each launch); got %d", h->graph_steps);
+    if (h->graph_steps & 3)
+        return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain a multiple of 4 fused steps (the launch phase is baked into each launch); got %d", h->graph_steps);
     CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
     return SEEKR2_B200_OK;
 }
 
 int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream) {
     if (!h || !h->graph_exec) return fail(SEEKR2_B200_ERR_INVALID, "no instantiated step graph");
-    if (h->parity != h->capture_parity0) return fail(SEEKR2_B200_ERR_INVALID, "slab parity differs from the one the graph was captured with");
+    if (h->phase != h->capture_phase0) return fail(SEEKR2_B200_ERR_INVALID, "launch phase differs from the one the graph was captured with");
     DeviceGuard guard(h->device);
     CUDA_TRY(cudaGraphLaunch(h->graph_exec, (cudaStream_t) stream));
     return SEEKR2_B200_OK;
@@ -687,8 +692,10 @@ int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int6
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaMemcpy(&h->d_state[anchor].time, &time, sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(&h->d_state[anchor].step_count, &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
-    for (int par = 0; par < 2; par++)
-        CUDA_TRY(cudaMemcpy(&h->d_step_shadow[par * h->cfg.num_anchors + anchor], &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
+    for (int ahead = 0; ahead < 2; ahead++) {       // the next launch reads slot `phase`, the one after it slot `phase + 1`
+        const int64_t v = step_count + ahead;
+        CUDA_TRY(cudaMemcpy(&h->d_step_shadow[((h->phase + ahead) & 3) * h->cfg.num_anchors + anchor], &v, sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
     return SEEKR2_B200_OK;
 }
 

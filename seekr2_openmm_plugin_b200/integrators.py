@@ -280,11 +280,11 @@ class _B200LangevinBase:
         """Queue ``steps`` steps on the context's stream (graph replays where possible); never blocks."""
         ctx = self.context
         done = 0
-        if self.useGraph and self.stepMode == "fused":
-            S = self.stepsPerGraph
+        if self.useGraph and self.stepMode == "fused" and self.stepsPerGraph >= 4:
+            S = self.stepsPerGraph // 4 * 4        # the launch phase (mod 4) is baked into every captured launch
             while steps - done >= S:
                 ri = self._prepare_random(S)
-                key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, self._prev)
+                key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, self._prev, self._steps_issued % 4)   # launch phase is baked in
                 if self._graph_key != key:
                     self._capture(S, ri)
                     self._graph_key = key
@@ -303,8 +303,8 @@ class _B200LangevinBase:
 
     def _capture(self, S: int, random_index0: int) -> None:
         ctx = self.context
-        if S % 2:
-            raise L.Seekr2Error(L.ERR_INVALID, "stepsPerGraph must be even")
+        if S % 4:
+            raise L.Seekr2Error(L.ERR_INVALID, "stepsPerGraph must be a multiple of 4")
         Np = ctx.padded_num_atoms
         bufs = ctx.buffers()
         L.check(L.lib.seekr2_b200_graph_begin(self._handle, ctx.stream_ptr))
