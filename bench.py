@@ -356,6 +356,36 @@ def main() -> None:
                                                     "note": "1 anchor x 64 atoms, CUDA graph of 32 steps"}
     A = A_saved
 
+    # ---- C2 / C3 (BASELINE.json configs[1], [2]): host-guest size, 2 520 atoms, host 147 / guest 15 atom centroid groups,
+    #      spheres at 0.3 / 0.5 nm, dt 2 fs, ONE anchor on the GPU: MMVT, Elber (reflect / transmit pair) and plain Langevin
+    def host_guest(kind: str):
+        host, guest = list(range(0, 147)), list(range(147, 162))
+        syn = H.pair_sphere_system(2520, host, guest, 0.3, 0.5, seed + 2, dt=0.002, tether_k=0.0)
+        H.place_pair_distance(syn, host, guest, 0.4)
+        if kind == "mmvt":
+            integ_h = H.make_mmvt_integrator(syn, "")
+        elif kind == "elber":
+            integ_h = s2.ElberLangevinIntegrator(300.0, 1.0, 0.002, "")
+            integ_h.addSrcMilestoneGroup(1)
+            integ_h.setEndOnSrcMilestone(False)
+        else:
+            integ_h = s2.LangevinIntegrator(300.0, 1.0, 0.002)
+        integ_h.setRandomNumberSeed(seed + 21 + rank)
+        integ_h.ringCapacity = 1 << 14
+        integ_h.setUseGraph(True, STEPS_PER_GRAPH)
+        ctx_h = s2.Context(syn.system, integ_h, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=1,
+                           randomPoolSteps=STEPS_PER_GRAPH)
+        ctx_h.setPositions(syn.positions)
+        ctx_h.setVelocities(syn.velocities)
+        t, _, _, _ = timed_run(ctx_h, integ_h, args.steps, W)
+        mode = integ_h.getDecisionMode()
+        return t * 1e3 / args.steps, mode
+    hg = {k: host_guest(k) for k in ("mmvt", "elber", "langevin")}
+    host_guest_c2 = {"workload": "C2/C3 host-guest size: 2520 atoms, 147 + 15 atom centroid groups, spheres 0.3 / 0.5 nm, dt 2 fs, 1 anchor, mixed",
+                     "mmvt_us_per_step": hg["mmvt"][0], "elber_us_per_step": hg["elber"][0], "plain_langevin_us_per_step": hg["langevin"][0],
+                     "mmvt_ns_per_day": 86400.0 / (hg["mmvt"][0] * 1e-6) * 0.002e-3, "elber_ns_per_day": 86400.0 / (hg["elber"][0] * 1e-6) * 0.002e-3,
+                     "decision_mode": hg["mmvt"][1]}
+
     # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---
     box = None
     if not args.no_box:
@@ -467,7 +497,7 @@ def main() -> None:
                 "ns_per_day_per_anchor": value / (A * world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches + fills, "roofline": roofline, "cpu_baseline": cpu,
                 "mmvt_over_plain_langevin": mmvt_over_langevin, "us_per_launch_by_integrator": variants,
-                "single_anchor_per_gpu": single_anchor, "box_100k": box, "api_call": api_call,
+                "single_anchor_per_gpu": single_anchor, "host_guest_c2": host_guest_c2, "box_100k": box, "api_call": api_call,
                 "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
                 "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
         emit(line)
