@@ -323,6 +323,10 @@ int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream);
 int seekr2_b200_drain_begin(seekr2_b200_handle h, int64_t max_records, void* stream);
 int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n,
                           int64_t* out_waiting);
+/* 1 if seekr2_b200_drain_end would return without waiting (the drain in flight has landed in host memory, or none is
+   in flight), 0 if the device has not got there yet, -1 on error.  Never blocks: lets a caller that issues one step
+   per call (the OpenMM adapter) collect records whenever they happen to be there.                            */
+int seekr2_b200_drain_ready(seekr2_b200_handle h);
 /* drain_begin + drain_end: blocks until everything queued on `stream` before the call has run.             */
 int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records,
                       int64_t* out_n, void* stream);

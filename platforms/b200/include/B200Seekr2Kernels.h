@@ -37,6 +37,17 @@ protected:
     void allocateScratch(bool oldVelm, bool oldDelta);
     OpenMM::CudaArray oldVelm, oldDelta;          /* multi-pass scratch (CudaSeekr2Kernels.cpp:618-643) */
     void drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc);
+    /* asynchronous drain (MMVT, SEEKR2_B200_ASYNC_DRAIN=1): execute() never waits for the device -- a drain is begun
+       behind each step's kernels and collected by a later execute() once it has landed; flushDrain() (blocking) runs
+       where the reference's files must be complete: computeKineticEnergy, statistics writes, destruction */
+    bool asyncDrain = false, drainPending = false;
+    int64_t collectPending(bool block);           /* records handed to writeRecords(); -1 = not ready */
+    void flushDrain();
+    void writeRecords(int64_t n);
+    void writeStatistics();
+    std::string drainFile, statisticsFile;
+    int drainKind = 0, drainNumSrc = 0;
+    std::vector<int32_t> drainLabels;
     OpenMM::CudaContext& cu;
     seekr2_b200_handle handle = nullptr;
     B200BoundarySet boundarySet;

@@ -12,6 +12,7 @@
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
 #include "openmm/cuda/CudaIntegrationUtilities.h"
+#include <cstdlib>
 #include <fstream>
 
 using namespace OpenMM;
@@ -19,6 +20,9 @@ namespace Seekr2Plugin {
 
 B200StepKernelBase::~B200StepKernelBase() {
     cu.setAsCurrent();                                            /* :74-80 */
+    if (handle && asyncDrain) {
+        try { flushDrain(); } catch (...) {}                      /* the crossings file is complete when the kernel goes away */
+    }
     seekr2_b200_destroy(handle);
 }
 
@@ -44,6 +48,9 @@ void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, i
     cfg.group_weights = boundarySet.groupWeights.data();
     cfg.num_boundaries = (int) boundarySet.boundaries.size();
     cfg.boundaries = boundarySet.boundaries.data();
+    /* asynchronous drain: MMVT only (Elber mirrors the context time every step), and not while crossing states are
+       saved (their atom order is the one of the crossing step, and OpenMM may reorder atoms before a late collection) */
+    if (const char* a = getenv("SEEKR2_B200_ASYNC_DRAIN")) asyncDrain = a[0] == '1' && cfg.kind == SEEKR2_B200_KIND_MMVT && saveStateFileName.empty();
     /* the ring is drained in the step that crossed, so two slots are plenty */
     cfg.save_state_slots = saveStateFileName.empty() ? 0 : 2;
     check(seekr2_b200_create(&cfg, &handle));
@@ -108,9 +115,64 @@ void B200StepKernelBase::stepMiddle(double temperature, double friction, double 
 }
 
 void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc) {
+    drainFile = file; drainKind = kind; drainLabels = labels; drainNumSrc = numSrc;
+    if (asyncDrain) {
+        /* collect the drain begun by an earlier step if it has landed (never waits), then queue one behind this step */
+        const int64_t n = drainPending ? collectPending(false) : -1;
+        if (n < 0) records.clear();                                /* nothing new this time */
+        if (!drainPending) {
+            check(seekr2_b200_drain_begin(handle, 4096, (void*) cu.getCurrentStream()));
+            drainPending = true;
+        }
+        return;
+    }
     records.resize(4096);
     int64_t n = 0;
     check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
+    writeRecords(n);
+}
+
+int64_t B200StepKernelBase::collectPending(bool block) {
+    if (!drainPending) return 0;
+    if (!block) {
+        const int ready = seekr2_b200_drain_ready(handle);
+        if (ready < 0) check(SEEKR2_B200_ERR_CUDA);
+        if (ready == 0) return -1;
+    }
+    records.resize(4096);
+    int64_t n = 0, waiting = 0;
+    check(seekr2_b200_drain_end(handle, records.data(), (int64_t) records.size(), &n, &waiting));
+    drainPending = false;
+    writeRecords(n);
+    return n;
+}
+
+void B200StepKernelBase::flushDrain() {
+    if (!asyncDrain || drainFile.empty()) return;
+    int64_t total = collectPending(true);
+    for (;;) {                                                     /* whatever was appended after the last drain_begin */
+        records.resize(4096);
+        int64_t n = 0;
+        check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
+        writeRecords(n);
+        total += n;
+        if (n < (int64_t) 4096) break;
+    }
+    if (total > 0) writeStatistics();
+}
+
+/* CudaSeekr2Kernels.cpp:313-345: rewritten whenever crossings have been logged */
+void B200StepKernelBase::writeStatistics() {
+    if (statisticsFile.empty()) return;
+    seekr2_b200_anchor_state st;
+    check(seekr2_b200_get_state(handle, 0, &st, (void*) cu.getCurrentStream()));
+    check(seekr2_b200_write_statistics(statisticsFile.c_str(), &st, drainLabels.data(), (int32_t) drainLabels.size()));
+}
+
+void B200StepKernelBase::writeRecords(int64_t n) {
+    const std::string& file = drainFile;
+    const int kind = drainKind, numSrc = drainNumSrc;
+    const std::vector<int32_t>& labels = drainLabels;
     if (n > 0) check(seekr2_b200_append_records(kind, file.c_str(), records.data(), n, 0, labels.data(), (int32_t) labels.size(), numSrc));
     records.resize((size_t) n);
     /* saveStateFileName: the crossed configuration, kept on the device before the bounce, goes to
@@ -151,6 +213,7 @@ void B200MmvtStepKernel<K, I, MIDDLE>::initialize(const System& system, const I&
     if (MIDDLE) allocateScratch(true, true);
     outputFileName = integrator.getOutputFileName();
     saveStatisticsFileName = integrator.getSaveStatisticsFileName();
+    statisticsFile = saveStatisticsFileName;
     for (int i = 0; i < integrator.getNumMilestoneGroups(); i++) milestoneGroups.push_back(integrator.getMilestoneGroup(i));
     check(seekr2_b200_write_header(SEEKR2_B200_KIND_MMVT, outputFileName.c_str()));          /* :158-171 */
 }
@@ -169,11 +232,9 @@ void B200MmvtStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& in
     if (MIDDLE) stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     else stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     drainTo(outputFileName, SEEKR2_B200_KIND_MMVT, milestoneGroups, 0);
-    if (!saveStatisticsFileName.empty() && !records.empty()) {     /* :313-345 */
-        seekr2_b200_anchor_state st;
-        check(seekr2_b200_get_state(handle, 0, &st, stream));
-        check(seekr2_b200_write_statistics(saveStatisticsFileName.c_str(), &st, milestoneGroups.data(), (int32_t) milestoneGroups.size()));
-    }
+    /* (asynchronous drain: `records` holds what an earlier step's drain delivered; the statistics only change on
+       crossings, so the file written now equals the one the reference wrote at the latest collected crossing) */
+    if (!records.empty()) writeStatistics();                       /* :313-345 */
     cu.setTime(cu.getTime() + integrator.getStepSize());           /* :362-365 */
     cu.setStepCount(cu.getStepCount() + 1);
     cu.reorderAtoms();
@@ -182,6 +243,7 @@ void B200MmvtStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& in
 
 template <class K, class I, bool MIDDLE>
 double B200MmvtStepKernel<K, I, MIDDLE>::computeKineticEnergy(ContextImpl&, const I& integrator) {
+    flushDrain();                                                  /* a natural synchronisation point: bring the files up to date */
     return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :368-370, :917-919 */
 }
 

@@ -117,6 +117,7 @@ SYMBOLS = {
     "seekr2_b200_graph_launch": (C.c_int, [_P, _P]),
     "seekr2_b200_drain": (C.c_int, [_P, C.POINTER(Record), C.c_int64, C.POINTER(C.c_int64), _P]),
     "seekr2_b200_drain_begin": (C.c_int, [_P, C.c_int64, _P]),
+    "seekr2_b200_drain_ready": (C.c_int, [_P]),
     "seekr2_b200_drain_end": (C.c_int, [_P, C.POINTER(Record), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "seekr2_b200_get_state": (C.c_int, [_P, C.c_int32, C.POINTER(AnchorState), _P]),
     "seekr2_b200_set_time": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int64, _P]),

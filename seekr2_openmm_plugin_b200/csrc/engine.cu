@@ -668,6 +668,17 @@ int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t
     return SEEKR2_B200_OK;
 }
 
+int seekr2_b200_drain_ready(seekr2_b200_handle h) {
+    if (!h) return -1;
+    if (!h->drain_pending) return 1;
+    DeviceGuard guard(h->device);
+    const cudaError_t e = cudaEventQuery(h->drain_event);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    fail(SEEKR2_B200_ERR_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(e));
+    return -1;
+}
+
 int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records, int64_t* out_n, void* stream) {
     if (!h || !out_n) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
     *out_n = 0;

@@ -127,6 +127,19 @@ def test_toy_mmvt_reference_platform_vs_b200_vs_oracle(cuda_device, tmp_path, ki
     assert "energyEvaluations 0 " in out["b200"][1] and f"energyEvaluations {steps + 1} " in out["ref"][1]
 
 
+@pytest.mark.parametrize("kind", ["mmvt", "mmvt_middle"])
+def test_adapter_asynchronous_drain_writes_the_same_files(cuda_device, tmp_path, kind, monkeypatch):
+    """SEEKR2_B200_ASYNC_DRAIN=1: the adapter's execute() never waits for the device (a drain is begun behind every step
+    and collected by a later step once it has landed; flushed at computeKineticEnergy / destruction).  Crossings file,
+    statistics file and final buffers still equal the reference CUDA platform's, which reads back and writes every step."""
+    monkeypatch.setenv("SEEKR2_B200_ASYNC_DRAIN", "1")          # read by the adapter only
+    syn = H.toy_system()
+    pool = H.gaussian_pool(H.SEED_BASE + 43, 3000 * 32)
+    out = run_both(tmp_path, syn, kind, "mixed", [1000, 1500, 500], pool, milestones=syn.milestone_groups, savestats=True)
+    lines, _ = assert_same_outputs(out, "mixed", 1, stats=True, min_lines=4)
+    assert "energyEvaluations 0 " in out["b200"][1]
+
+
 def test_corner_bounce_rawstyle_restart_counter(cuda_device, tmp_path):
     for name, syn, steps, ms in (("corner", S.ballistic_toy(extra_plane=True), 400, [1, 2, 3]), ("raw", S.ballistic_toy(raw_style=True), 200, [1])):
         d = tmp_path / name
