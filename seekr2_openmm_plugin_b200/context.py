@@ -126,22 +126,34 @@ class Context:
             raise L.Seekr2Error(L.ERR_INVALID, f"expected an array of shape [A,]N,3; got {arr.shape}")
         return arr
 
+    def _to_device_f64(self, arr) -> torch.Tensor:
+        """[A, N, 3] float64 on the device; a single configuration is uploaded once and replicated there."""
+        arr = np.asarray(arr, dtype=np.float64)
+        if arr.ndim == 3 and arr.shape[0] == 1 and self.num_anchors > 1:
+            arr = arr[0]
+        if arr.ndim == 2:
+            if arr.shape != (self.num_atoms, 3):
+                raise L.Seekr2Error(L.ERR_INVALID, f"expected an array of shape [A,]N,3; got {arr.shape}")
+            return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)[None].expand(self.num_anchors, -1, -1)
+        if arr.shape != (self.num_anchors, self.num_atoms, 3):
+            raise L.Seekr2Error(L.ERR_INVALID, f"expected an array of shape [A,]N,3; got {arr.shape}")
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
     def setPositions(self, positions) -> None:
-        """posq = (real) x; posqCorrection = x - (real) x in mixed precision (OpenMM CudaContext)."""
-        x = self._broadcast(positions)
+        """posq = (real) x; posqCorrection = x - (real) x in mixed precision (OpenMM CudaContext).  One upload of the
+        doubles; the split is done on the device (same IEEE roundings as on the host)."""
         self.stream.synchronize()
-        hi = x.astype(np.float64 if self.precision == L.DOUBLE else np.float32)
-        self.posq[:, : self.num_atoms, :3] = torch.as_tensor(np.array(hi, copy=True), device=self.device)
+        x = self._to_device_f64(positions)
+        hi = x.to(self.real_dtype)
+        self.posq[:, : self.num_atoms, :3] = hi
         if self.posq_correction is not None:
-            lo = (x - hi.astype(np.float64)).astype(np.float32)
-            self.posq_correction[:, : self.num_atoms, :3] = torch.as_tensor(lo, device=self.device)
+            self.posq_correction[:, : self.num_atoms, :3] = (x - hi.to(torch.float64)).to(torch.float32)
         torch.cuda.synchronize(self.device)
         self.groups_dirty = True
 
     def setVelocities(self, velocities) -> None:
-        v = self._broadcast(velocities)
         self.stream.synchronize()
-        self.velm[:, : self.num_atoms, :3] = torch.as_tensor(np.array(v, copy=True), dtype=self.mixed_dtype, device=self.device)
+        self.velm[:, : self.num_atoms, :3] = self._to_device_f64(velocities).to(self.mixed_dtype)
         torch.cuda.synchronize(self.device)
         self.groups_dirty = True
 
