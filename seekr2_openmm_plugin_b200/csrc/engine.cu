@@ -157,6 +157,7 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
         gather_groups_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->phase & 1);
     }
     decide_kernel<P, SEEKR2_B200_KIND_MMVT, 1><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
+    refresh_shadow_kernel<<<(h->cfg.num_anchors + 127) / 128, 128, 0, s>>>(h->dev, h->phase);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }

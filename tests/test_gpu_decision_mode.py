@@ -88,3 +88,32 @@ def test_auto_mode_picks_by_launch_size(cuda_device):
     integ.setDecisionMode("local")
     with pytest.raises(s2.Seekr2Error):
         s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+
+
+@pytest.mark.parametrize("mode", ["local", "handoff"])
+def test_two_pass_and_fused_steps_interleave_on_one_random_stream(cuda_device, mode):
+    """In-kernel Philox normals are keyed by the step index.  Two-pass steps advance the device clock but not the fused
+    kernels' four-phase step-index slots; seekr2_b200_sync_groups (mandatory before the next fused step) refreshes them,
+    so a run that switches between the forms equals an all-fused run bit for bit."""
+    A, n = 2, 1200
+    out = {}
+    for plan in ("fused", "mixed"):
+        syn, positions = _shell_workload(A, n, H.SEED_BASE + 63)
+        integ = H.make_mmvt_integrator(syn, "")
+        integ.setDecisionMode(mode)
+        integ.setRandomNumberSeed(21)
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
+        ctx.setPositions(positions)
+        ctx.setVelocities(syn.velocities)
+        if plan == "fused":
+            integ.step(150)
+        else:
+            for form, steps in (("fused", 37), ("two_pass", 41), ("fused", 30), ("two_pass", 2), ("fused", 40)):
+                integ.setStepMode(form)
+                integ.step(steps)
+        out[plan] = ([H.download(ctx, a) for a in range(A)], [H.records_as_tuples(integ.getRecords(a)) for a in range(A)],
+                     [integ.getAnchorState(a).step_count for a in range(A)])
+    assert out["fused"][1] == out["mixed"][1] and out["fused"][2] == out["mixed"][2] == [150] * A
+    assert sum(len(r) for r in out["fused"][1]) >= 2
+    for a in range(A):
+        H.assert_state_equal(out["fused"][0][a], out["mixed"][0][a], n, f"all-fused vs interleaved, anchor {a}")
