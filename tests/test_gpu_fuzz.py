@@ -1,0 +1,139 @@
+"""Randomised differential test: random boundary sets (centroid-pair spheres, fixed-centre spheres, axis planes; step and
+raw style; explicit weights; groups of 1 .. 140 atoms, some spanning several warps, some sharing atoms), random precision,
+scheme and variant -- the fused step in BOTH decision modes and the two-pass form must equal the CPU oracle bit for bit
+(state, crossing records, statistics).  Thresholds are placed a hair from the starting values so that every case bounces."""
+import numpy as np
+import pytest
+
+import helpers as H
+import scenarios as S
+from helpers import L, s2
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(200, 2600))
+    pos, vel, masses = H.lattice_system(n, 1000 + seed)
+    if rng.random() < 0.3:                                   # a few immobile particles
+        for i in rng.choice(n, 3, replace=False):
+            masses[i] = 0.0
+            vel[i] = 0.0
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    bit = 1.0
+    groups_used = 0
+    labels = []
+
+    def centroid(idx, w=None):
+        ww = masses[idx] if w is None else np.asarray(w)
+        return (pos[idx] * ww[:, None]).sum(0) / ww.sum()
+
+    def pick(size):
+        idx = rng.choice(n, size, replace=False)
+        idx = idx[masses[idx] > 0] if rng.random() < 0.5 else idx
+        return [int(i) for i in (idx if len(idx) else [int(np.argmax(masses))])]
+
+    n_forces = int(rng.integers(1, 4))
+    for _ in range(n_forces):
+        kind = rng.choice(["pair", "fixed", "plane"])
+        raw = rng.random() < 0.15
+        margin = float(rng.uniform(0.0005, 0.003))
+        sizes = [int(rng.choice([1, 3, 11, 33, 70, 140])) for _ in range(2)]
+        if groups_used + 2 > 14 or bit > 8:
+            break
+        if kind == "pair":
+            f = s2.CustomCentroidBondForce(2, "k*(distance(g1,g2)^2-radius^2)" if raw else "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+            a, b = pick(sizes[0]), pick(sizes[1])
+            wa = [float(x) for x in rng.uniform(0.5, 2.0, len(a))] if rng.random() < 0.4 else None
+            ga = f.addGroup(a, wa) if wa else f.addGroup(a)
+            gb = f.addGroup(b)
+            d = float(np.linalg.norm(centroid(a, wa) - centroid(b)))
+            params_in, params_out = ([-1.0, max(d - margin, 1e-4)], [1.0, d + margin])
+            names = ("k", "radius") if raw else ("bitcode", "k", "radius")
+            for p in names:
+                f.addPerBondParameter(p)
+            if raw:
+                f.addBond([ga, gb], params_out)
+            else:
+                f.addBond([ga, gb], [bit] + params_in); bit *= 2
+                f.addBond([ga, gb], [bit] + params_out); bit *= 2
+            groups_used += 2
+        elif kind == "fixed":
+            f = s2.CustomCentroidBondForce(1, "k*((x1-cx)^2+(y1-cy)^2+(z1-cz)^2-radius^2)" if raw else "bitcode*step(k*((x1-cx)^2+(y1-cy)^2+(z1-cz)^2-radius^2))")
+            a = pick(sizes[0])
+            ga = f.addGroup(a)
+            c = centroid(a) + rng.uniform(-0.3, 0.3, 3)
+            d = float(np.linalg.norm(centroid(a) - c))
+            names = ("k", "cx", "cy", "cz", "radius") if raw else ("bitcode", "k", "cx", "cy", "cz", "radius")
+            for p in names:
+                f.addPerBondParameter(p)
+            tail = [1.0, float(c[0]), float(c[1]), float(c[2]), d + margin]
+            f.addBond([ga], tail if raw else [bit] + tail)
+            if not raw:
+                bit *= 2
+            groups_used += 1
+        else:
+            axis = "xyz"[int(rng.integers(0, 3))]
+            f = s2.CustomCentroidBondForce(1, f"k*({axis}1-bound)" if raw else f"bitcode*step(k*({axis}1-bound))")
+            a = pick(sizes[0])
+            ga = f.addGroup(a)
+            c = centroid(a)["xyz".index(axis)]
+            names = ("k", "bound") if raw else ("bitcode", "k", "bound")
+            for p in names:
+                f.addPerBondParameter(p)
+            sign = float(rng.choice([-1.0, 1.0]))
+            tail = [sign, float(c + sign * margin)]
+            f.addBond([ga], tail if raw else [bit] + tail)
+            if not raw:
+                bit *= 2
+            groups_used += 1
+        f.setForceGroup(1)
+        system.addForce(f)
+    num_bits = max(1, int(np.log2(bit))) if bit > 1 else 1
+    labels = list(range(1, num_bits + 1))
+    syn = H.Synthetic(system, pos, vel, masses, None, labels, 0.0, 0.002)
+    precision = [L.SINGLE, L.MIXED, L.MIXED, L.DOUBLE][int(rng.integers(0, 4))]
+    middle = bool(rng.random() < 0.4)
+    variant = "reference" if rng.random() < 0.25 else "cuda"
+    steps = int(rng.integers(60, 200))
+    return syn, precision, middle, variant, steps, n
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_boundary_sets_match_the_oracle(cuda_device, seed):
+    syn, precision, middle, variant, steps, n = _random_case(seed)
+    npad = (n + 31) // 32 * 32
+    pool = H.gaussian_pool(7000 + seed, steps * npad)
+    m = len(syn.milestone_groups)
+    rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, "", variant, middle=middle), precision, steps, pool)
+    for mode, decision in (("fused", "local"), ("fused", "handoff"), ("two_pass", "auto")):
+        integ = H.make_mmvt_integrator(syn, "", variant, middle=middle)
+        if decision != "auto":
+            try:
+                integ.setDecisionMode(decision)
+                grc, ctx, gb = S.run_gpu(syn, integ, precision, steps, pool, mode=mode, graph=8 if seed % 2 else 0)
+            except s2.Seekr2Error as e:                 # more than 256 padded slots: LOCAL is refused, the hand-off covers it
+                assert decision == "local" and "group slots" in str(e)
+                continue
+        else:
+            grc, ctx, gb = S.run_gpu(syn, integ, precision, steps, pool, mode=mode)
+        assert rc == grc, (seed, mode, decision)
+        if rc != 0:
+            continue                                    # e.g. a raw-style term positive at step 0: both sides refuse the start
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (seed, mode, decision)
+        H.assert_state_equal(ob, gb, n, f"seed {seed} {mode} {decision}")
+        assert H.stats_tuple(o.state(), m) == H.stats_tuple(integ.getAnchorState(0), m), (seed, mode, decision)
+
+
+def test_fuzz_cases_do_bounce(cuda_device):
+    """The generator is only useful if its cases cross boundaries: most of them must."""
+    bounced = 0
+    for seed in range(16):
+        syn, precision, middle, variant, steps, n = _random_case(seed)
+        pool = H.gaussian_pool(7000 + seed, steps * ((n + 31) // 32 * 32))
+        rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, "", variant, middle=middle), precision, steps, pool)
+        bounced += rc == 0 and o.state().num_bounce_steps > 0
+    assert bounced >= 8, bounced
