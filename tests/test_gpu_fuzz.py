@@ -137,3 +137,68 @@ def test_fuzz_cases_do_bounce(cuda_device):
         rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, "", variant, middle=middle), precision, steps, pool)
         bounced += rc == 0 and o.state().num_bounce_steps > 0
     assert bounced >= 8, bounced
+
+
+def _random_elber_case(seed):
+    """Thermal solvated system, 2-4 milestone forces in their own force groups (one source, the rest destinations), each a
+    centroid-pair sphere a hair outside / inside the starting distance: the run crosses the source (clock reset or end)
+    and usually ends on a destination within a few hundred steps."""
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.integers(300, 2200))
+    pos, vel, masses = H.lattice_system(n, 3000 + seed)
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    a = [int(i) for i in rng.choice(n, int(rng.choice([1, 5, 20, 100])), replace=False)]      # 100: more than 256 padded slots
+    b = [int(i) for i in rng.choice(n, int(rng.choice([1, 9, 30])), replace=False)]           #      in total -> hand-off only
+    ca = (pos[a] * masses[a][:, None]).sum(0) / masses[a].sum()
+    cb = (pos[b] * masses[b][:, None]).sum(0) / masses[b].sum()
+    d = float(np.linalg.norm(ca - cb))
+    k = int(rng.integers(2, 5))
+    margins = sorted(float(x) for x in rng.uniform(0.0003, 0.004, k))
+    for g in range(k):
+        f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+        ga, gb = f.addGroup(a), f.addGroup(b)
+        for p in ("bitcode", "k", "radius"):
+            f.addPerBondParameter(p)
+        sign = 1.0 if g % 2 == 0 else -1.0                     # alternate outside / inside surfaces
+        f.addBond([ga, gb], [1.0, sign, max(d + sign * margins[g], 1e-4)])
+        f.setForceGroup(g + 1)
+        system.addForce(f)
+    syn = H.Synthetic(system, pos, vel, masses, None, [], 0.0, 0.002)
+    middle = bool(rng.random() < 0.5)
+    end_on_src = bool(rng.random() < 0.3)
+    precision = [L.SINGLE, L.MIXED, L.DOUBLE][int(rng.integers(0, 3))]
+    variant = "reference" if rng.random() < 0.25 else "cuda"
+    steps = int(rng.integers(80, 260))
+
+    def make():
+        integ = (s2.ElberLangevinMiddleIntegrator if middle else s2.ElberLangevinIntegrator)(300.0, 1.0, 0.002, "")
+        integ.addSrcMilestoneGroup(1)
+        for g in range(2, k + 1):
+            integ.addDestMilestoneGroup(g)
+        integ.setEndOnSrcMilestone(end_on_src)
+        integ.setVariant(variant)
+        return integ
+    return syn, make, precision, steps, n
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_elber_cases_match_the_oracle(cuda_device, seed):
+    syn, make, precision, steps, n = _random_elber_case(seed)
+    pool = H.gaussian_pool(9000 + seed, steps * ((n + 31) // 32 * 32))
+    rc, o, ob = S.run_oracle(syn, make(), precision, steps, pool)
+    for mode, decision in (("fused", "local"), ("fused", "handoff"), ("two_pass", "auto")):
+        integ = make()
+        integ.setDecisionMode(decision)
+        try:
+            grc, ctx, gb = S.run_gpu(syn, integ, precision, steps, pool, mode=mode, graph=8 if seed % 2 else 0)
+        except s2.Seekr2Error as e:                     # more than 256 padded slots: LOCAL is refused, the hand-off covers it
+            assert decision == "local" and "group slots" in str(e)
+            continue
+        assert rc == grc == 0, (seed, mode, decision)
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (seed, mode, decision)
+        H.assert_state_equal(ob, gb, n, f"elber seed {seed} {mode} {decision}")
+        so, sg = o.state(), integ.getAnchorState(0)
+        assert (so.time, so.step_count, so.crossing_counter, so.crossed_src, so.end_simulation) == \
+               (sg.time, sg.step_count, sg.crossing_counter, sg.crossed_src, sg.end_simulation), (seed, mode, decision)
