@@ -154,6 +154,10 @@ void seekr2_oracle_destroy(seekr2_oracle* o) {
 /* Builds the oracle for one anchor of a configuration (the same struct the product takes). */
 seekr2_oracle* seekr2_oracle_create(const seekr2_b200_config* cfg, int anchor) {
     if (!cfg || anchor < 0 || anchor >= cfg->num_anchors) return NULL;
+    /* the same limits the engine enforces (seekr2_b200_create): fixed-size tables below */
+    if (cfg->num_groups < 0 || cfg->num_groups > SEEKR2_B200_MAX_GROUPS || cfg->num_boundaries < 0 || cfg->num_boundaries > SEEKR2_B200_MAX_BOUNDARIES ||
+        cfg->num_milestone_groups < 0 || cfg->num_milestone_groups > SEEKR2_B200_MAX_MILESTONES ||
+        cfg->num_src < 0 || cfg->num_dest < 0 || cfg->num_src + cfg->num_dest > SEEKR2_B200_MAX_ELBER) return NULL;
     seekr2_oracle* o = (seekr2_oracle*) calloc(1, sizeof(seekr2_oracle));
     o->kind = cfg->kind; o->precision = cfg->precision; o->variant = cfg->variant; o->flags = cfg->flags; o->scheme = cfg->scheme;
     o->numAtoms = cfg->num_atoms; o->paddedNumAtoms = cfg->padded_num_atoms;

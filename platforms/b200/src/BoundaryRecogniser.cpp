@@ -40,21 +40,29 @@ Typed recognise(std::string e, int numGroups) {
 
 B200BoundarySet recogniseBoundaries(const System& system) {
     B200BoundarySet out;
+    /* identical groups (same particles, same weights) are lowered once: the reference's examples give every milestone
+       Force its own copies of the same two groups (demo3:37-45), and the engine takes at most SEEKR2_B200_MAX_GROUPS */
+    std::map<std::pair<std::vector<int>, std::vector<double>>, int> seen;
     for (int f = 0; f < system.getNumForces(); f++) {
         const auto* force = dynamic_cast<const CustomCentroidBondForce*>(&system.getForce(f));
         if (force == nullptr) continue;
         if (force->usesPeriodicBoundaryConditions()) throw OpenMMException("B200 SEEKR2 plugin: periodic centroid boundaries are not supported");
         const Typed t = recognise(force->getEnergyFunction(), force->getNumGroupsPerBond());
-        const int base = (int) out.groupOffsets.size() - 1;
+        std::vector<int> remap;
         for (int g = 0; g < force->getNumGroups(); g++) {
             std::vector<int> particles; std::vector<double> weights;
             force->getGroupParameters(g, particles, weights);
-            for (size_t i = 0; i < particles.size(); i++) {
-                out.groupAtoms.push_back(particles[i]);
-                /* without explicit weights a centroid group is mass weighted */
-                out.groupWeights.push_back(weights.empty() ? system.getParticleMass(particles[i]) : weights[i]);
+            /* without explicit weights a centroid group is mass weighted */
+            std::vector<double> w(particles.size());
+            for (size_t i = 0; i < particles.size(); i++) w[i] = weights.empty() ? system.getParticleMass(particles[i]) : weights[i];
+            const auto key = std::make_pair(particles, w);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (int) out.groupOffsets.size() - 1).first;
+                for (size_t i = 0; i < particles.size(); i++) { out.groupAtoms.push_back(particles[i]); out.groupWeights.push_back(w[i]); }
+                out.groupOffsets.push_back((int32_t) out.groupAtoms.size());
             }
-            out.groupOffsets.push_back((int32_t) out.groupAtoms.size());
+            remap.push_back(it->second);
         }
         std::map<std::string, int> index;
         for (int p = 0; p < force->getNumPerBondParameters(); p++) index[force->getPerBondParameterName(p)] = p;
@@ -65,7 +73,7 @@ B200BoundarySet recogniseBoundaries(const System& system) {
             force->getBondParameters(b, groups, params);
             seekr2_b200_boundary bd{};
             bd.type = t.type; bd.style = t.style; bd.axis = t.axis; bd.force_group = force->getForceGroup();
-            for (size_t g = 0; g < groups.size() && g < 6; g++) bd.groups[g] = base + groups[g];
+            for (size_t g = 0; g < groups.size() && g < 6; g++) bd.groups[g] = remap[groups[g]];
             bd.bitcode = value(params, "bitcode", 1.0);
             bd.k = t.kSign * value(params, "k", 1.0);
             bd.threshold = value(params, t.thr, 0.0);

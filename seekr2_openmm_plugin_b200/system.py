@@ -185,7 +185,9 @@ class CustomCentroidBondForce(Force):
         return len(self.bonds)
 
     # -- lowering ---------------------------------------------------------------------------
-    def typed_boundaries(self, anchor: int, group_base: int) -> List[L.Boundary]:
+    def typed_boundaries(self, anchor: int, group_base, remap: Optional[Sequence[int]] = None) -> List[L.Boundary]:
+        """``remap[g]`` = index of this Force's group g in the lowered (de-duplicated) group table; without it the
+        groups sit at ``group_base + g``."""
         out = []
         t = self._typed
         for bi, (groups, params) in enumerate(self.bonds):
@@ -197,7 +199,7 @@ class CustomCentroidBondForce(Force):
             b.type = t.cv_type
             b.style = t.style
             for gi, g in enumerate(groups[:6]):
-                b.groups[gi] = group_base + g
+                b.groups[gi] = remap[g] if remap is not None else group_base + g
             b.axis = t.axis
             b.force_group = self.getForceGroup()
             b.bitcode = p.get("bitcode", 1.0)
@@ -232,16 +234,22 @@ def lower_boundaries(system: System, num_anchors: int) -> LoweredBoundaries:
     offsets, atoms, weights = [0], [], []
     per_anchor: List[List[L.Boundary]] = [[] for _ in range(num_anchors)]
     masses = system.masses
-    for force in system._forces:
+    seen = {}            # identical groups (same atoms, same weights) are lowered once: the reference's examples give every
+    for force in system._forces:      # milestone Force its own copies of the same two groups (demo3:37-45)
         if not isinstance(force, CustomCentroidBondForce):
             continue
-        base = len(offsets) - 1
+        remap = []
         for indices, w in force.groups:
-            atoms.extend(indices)
             # OpenMM: without explicit weights a centroid group is mass weighted
-            weights.extend(w if w is not None else [masses[i] for i in indices])
-            offsets.append(len(atoms))
+            ww = [float(x) for x in (w if w is not None else [masses[i] for i in indices])]
+            key = (tuple(int(i) for i in indices), tuple(ww))
+            if key not in seen:
+                seen[key] = len(offsets) - 1
+                atoms.extend(indices)
+                weights.extend(ww)
+                offsets.append(len(atoms))
+            remap.append(seen[key])
         for a in range(num_anchors):
-            per_anchor[a].extend(force.typed_boundaries(a, base))
+            per_anchor[a].extend(force.typed_boundaries(a, 0, remap))
     return LoweredBoundaries(np.asarray(offsets, dtype=np.int32), np.asarray(atoms, dtype=np.int32),
                              np.asarray(weights, dtype=np.float64), per_anchor)

@@ -202,3 +202,42 @@ def test_random_elber_cases_match_the_oracle(cuda_device, seed):
         so, sg = o.state(), integ.getAnchorState(0)
         assert (so.time, so.step_count, so.crossing_counter, so.crossed_src, so.end_simulation) == \
                (sg.time, sg.step_count, sg.crossing_counter, sg.crossed_src, sg.end_simulation), (seed, mode, decision)
+
+
+def test_31_milestone_bits_many_surfaces_at_once(cuda_device):
+    """The reference's limit: 31 bit codes (README.md:331-333), here on 8 groups, with thresholds so close to the start that
+    steps cross several surfaces at once (corner bounces, bit strings beyond float precision: (int)(float)value is decoded the
+    same way on both sides)."""
+    n = 400
+    pos, vel, masses = H.lattice_system(n, 4242)
+    rng = np.random.default_rng(99)
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    groups = [[int(i) for i in rng.choice(n, size, replace=False)] for size in (1, 2, 3, 5, 8, 13, 21, 30)]
+    for b in range(31):
+        axis = "xyz"[b % 3]
+        f = s2.CustomCentroidBondForce(1, f"bitcode*step(k*({axis}1-bound))")
+        idx = groups[b % len(groups)]
+        g = f.addGroup(idx)
+        for p in ("bitcode", "k", "bound"):
+            f.addPerBondParameter(p)
+        c = float((pos[idx] * masses[idx][:, None]).sum(0)[b % 3] / masses[idx].sum())
+        sign = 1.0 if b % 2 else -1.0
+        f.addBond([g], [float(2 ** b), sign, c + sign * float(rng.uniform(0.002, 0.012))])
+        f.setForceGroup(1)
+        system.addForce(f)
+    syn = H.Synthetic(system, pos, vel, masses, None, list(range(1, 32)), 0.0, 0.002)
+    steps = 300
+    pool = H.gaussian_pool(4243, steps * ((n + 31) // 32 * 32))
+    rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, ""), L.MIXED, steps, pool)
+    assert rc == 0 and o.state().num_bounce_steps >= 5
+    assert max(r.num_surfaces for r in o.records()) >= 2, "some step must cross several surfaces"
+    for mode, decision in (("fused", "local"), ("fused", "handoff"), ("two_pass", "auto")):
+        integ = H.make_mmvt_integrator(syn, "")
+        integ.setDecisionMode(decision)
+        grc, ctx, gb = S.run_gpu(syn, integ, L.MIXED, steps, pool, mode=mode, graph=8)
+        assert grc == 0
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (mode, decision)
+        H.assert_state_equal(ob, gb, n, f"31 bits {mode} {decision}")
+        assert H.stats_tuple(o.state(), 31) == H.stats_tuple(integ.getAnchorState(0), 31), (mode, decision)
