@@ -241,3 +241,92 @@ def test_31_milestone_bits_many_surfaces_at_once(cuda_device):
         assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (mode, decision)
         H.assert_state_equal(ob, gb, n, f"31 bits {mode} {decision}")
         assert H.stats_tuple(o.state(), 31) == H.stats_tuple(integ.getAnchorState(0), 31), (mode, decision)
+
+
+@pytest.mark.parametrize("sizes", [(128, 128), (224, 32), (97, 33), (256,)])
+def test_local_mode_at_its_slot_limit(cuda_device, sizes):
+    """256 padded group slots is the most the LOCAL kernel takes (512-thread blocks: 256 streaming + 256 slot threads);
+    groups that fill whole warps exactly, a group spanning seven warps, one 256-atom group on a plane."""
+    n = 1500
+    pos, vel, masses = H.lattice_system(n, 5150 + sum(sizes))
+    rng = np.random.default_rng(len(sizes) * 100 + sizes[0])
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    idx = [int(i) for i in rng.permutation(n)[: sum(sizes)]]
+    parts = [idx[: sizes[0]], idx[sizes[0]:]] if len(sizes) == 2 else [idx]
+    cen = [(pos[p] * masses[p][:, None]).sum(0) / masses[p].sum() for p in parts]
+    if len(sizes) == 2:
+        f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+        ga, gb = f.addGroup(parts[0]), f.addGroup(parts[1])
+        for p in ("bitcode", "k", "radius"):
+            f.addPerBondParameter(p)
+        d = float(np.linalg.norm(cen[0] - cen[1]))
+        f.addBond([ga, gb], [1.0, -1.0, d - 0.0002])
+        f.addBond([ga, gb], [2.0, 1.0, d + 0.0002])
+    else:
+        f = s2.CustomCentroidBondForce(1, "bitcode*step(k*(x1-bound))")
+        ga = f.addGroup(parts[0])
+        for p in ("bitcode", "k", "bound"):
+            f.addPerBondParameter(p)
+        f.addBond([ga], [1.0, -1.0, float(cen[0][0]) - 0.0001])
+        f.addBond([ga], [2.0, 1.0, float(cen[0][0]) + 0.0001])
+    f.setForceGroup(1)
+    system.addForce(f)
+    syn = H.Synthetic(system, pos, vel, masses, None, [1, 2], 0.0, 0.002)
+    steps = 400
+    pool = H.gaussian_pool(5151, steps * ((n + 31) // 32 * 32))
+    rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, ""), L.MIXED, steps, pool)
+    assert rc == 0 and o.state().num_bounce_steps >= 2, o.state().num_bounce_steps
+    for decision in ("local", "handoff"):
+        integ = H.make_mmvt_integrator(syn, "")
+        integ.setDecisionMode(decision)
+        grc, ctx, gb_ = S.run_gpu(syn, integ, L.MIXED, steps, pool, graph=8)
+        assert grc == 0 and integ.getDecisionMode() == decision
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), decision
+        H.assert_state_equal(ob, gb_, n, f"slot limit {sizes} {decision}")
+
+
+def test_sixteen_elber_milestones(cuda_device):
+    """SEEKR2_B200_MAX_ELBER = 16: one source and fifteen destination milestones (each its own Force and force group, all on
+    the same two centroid groups, which are lowered once), thermal run until a destination ends it."""
+    n = 900
+    pos, vel, masses = H.lattice_system(n, 6161)
+    a, b = list(range(3, 14)), list(range(40, 49))
+    ca = (pos[a] * masses[a][:, None]).sum(0) / masses[a].sum()
+    cb = (pos[b] * masses[b][:, None]).sum(0) / masses[b].sum()
+    d = float(np.linalg.norm(ca - cb))
+    system = s2.System()
+    for m in masses:
+        system.addParticle(float(m))
+    for g in range(16):
+        f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+        ga, gb = f.addGroup(a), f.addGroup(b)
+        for p in ("bitcode", "k", "radius"):
+            f.addPerBondParameter(p)
+        sign = 1.0 if g % 2 == 0 else -1.0
+        f.addBond([ga, gb], [1.0, sign, d + sign * 0.0004 * (g + 1)])
+        f.setForceGroup(g + 1)
+        system.addForce(f)
+    syn = H.Synthetic(system, pos, vel, masses, None, [], 0.0, 0.002)
+
+    def make():
+        integ = s2.ElberLangevinIntegrator(300.0, 1.0, 0.002, "")
+        integ.addSrcMilestoneGroup(1)
+        for g in range(2, 17):
+            integ.addDestMilestoneGroup(g)
+        integ.setEndOnSrcMilestone(False)
+        return integ
+    steps = 400
+    pool = H.gaussian_pool(6162, steps * ((n + 31) // 32 * 32))
+    rc, o, ob = S.run_oracle(syn, make(), L.MIXED, steps, pool)
+    assert rc == 0 and o.state().end_simulation == 1 and len(o.records()) >= 1
+    for mode, decision in (("fused", "local"), ("fused", "handoff"), ("two_pass", "auto")):
+        integ = make()
+        integ.setDecisionMode(decision)
+        grc, ctx, gb_ = S.run_gpu(syn, integ, L.MIXED, steps, pool, mode=mode, graph=8)
+        assert grc == 0
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (mode, decision)
+        H.assert_state_equal(ob, gb_, n, f"16 elber milestones {mode} {decision}")
+        so, sg = o.state(), integ.getAnchorState(0)
+        assert (so.time, so.crossing_counter, so.crossed_src, so.end_simulation) == (sg.time, sg.crossing_counter, sg.crossed_src, sg.end_simulation)
