@@ -301,9 +301,9 @@ def main() -> None:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this very
-    # workload (profiles/r01d_fused_step_ncu_full.txt: 260.2 MB read + 134.2 MB written; the tail of the writes is
+    # workload (profiles/r01d_fused_step_ncu_full.txt: 260.2 MB read + 132.9 MB written; the tail of the writes is
     # still in L2 when the kernel ends); null otherwise
-    traffic = 394.4e6 if (A, args.atoms) == (128, N_ATOMS) else None
+    traffic = 393.1e6 if (A, args.atoms) == (128, N_ATOMS) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>" if integ.getDecisionMode() == "handoff" else "fused_local_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
