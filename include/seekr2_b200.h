@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 7
+#define SEEKR2_B200_ABI_VERSION 8
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -327,13 +327,19 @@ int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t
    in flight), 0 if the device has not got there yet, -1 on error.  Never blocks: lets a caller that issues one step
    per call (the OpenMM adapter) collect records whenever they happen to be there.                            */
 int seekr2_b200_drain_ready(seekr2_b200_handle h);
+/* Every drain also carries each anchor's clock: the context time and step count the device held when the pack kernel ran
+   (cu.getTime() / cu.getStepCount() of the reference, which Elber resets on the device, CudaSeekr2Kernels.cpp:545).  Valid
+   after seekr2_b200_drain_end; reads host memory only, never blocks.  Lets the OpenMM adapter mirror Context time without a
+   read-back per step.                                                                                              */
+int seekr2_b200_drain_clock(seekr2_b200_handle h, int32_t anchor, double* time, int64_t* step_count);
 /* drain_begin + drain_end: blocks until everything queued on `stream` before the call has run.             */
 int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records,
                       int64_t* out_n, void* stream);
 
 int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anchor_state* out,
                           void* stream);
-/* Context::setTime / setStepCount analogue (used by reinitialize and by tests)                     */
+/* Context::setTime / setStepCount analogue (used by reinitialize, the OpenMM adapter and tests): one small
+   launch on `stream` carrying the values as parameters -- stream-ordered, never blocks the host.     */
 int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int64_t step_count,
                          void* stream);
 

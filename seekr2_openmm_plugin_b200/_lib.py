@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SEEKR2_B200_LIBRARY") or os.path.join(_HERE, "libseekr2_b200.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -118,6 +118,7 @@ SYMBOLS = {
     "seekr2_b200_drain": (C.c_int, [_P, C.POINTER(Record), C.c_int64, C.POINTER(C.c_int64), _P]),
     "seekr2_b200_drain_begin": (C.c_int, [_P, C.c_int64, _P]),
     "seekr2_b200_drain_ready": (C.c_int, [_P]),
+    "seekr2_b200_drain_clock": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "seekr2_b200_drain_end": (C.c_int, [_P, C.POINTER(Record), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "seekr2_b200_get_state": (C.c_int, [_P, C.c_int32, C.POINTER(AnchorState), _P]),
     "seekr2_b200_set_time": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int64, _P]),

@@ -57,7 +57,20 @@ struct EngineDev {
     void* snap_posq;             // real4 [A][slots][Np]   pre-bounce positions of the last crossings
     void* snap_corr;             // real4 [A][slots][Np]   (MIXED only)
     void* snap_velm;             // mixed4[A][slots][Np]
+    // LOCAL decision mode (fused_local_kernel, finish_local_kernel)
+    int slot_layout;             // kLayoutAligned: every group padded to whole warps; kLayoutPacked: all groups in one warp
+    int slot_threads;            // slot threads per block: 32 (packed, or no slots at all) or num_slots (aligned, a multiple of 32)
+    int local_stream_threads;    // streaming threads per block (a multiple of 32); one atom per thread and tile
+    int local_tiles;             // ceil(num_atoms / local_stream_threads): a block walks tiles blockIdx.x, + gridDim.x, ...
+    int group_warp_begin[SEEKR2_B200_MAX_GROUPS + 1];   // aligned layout: slot warps [begin[g], begin[g+1]) hold group g
+    int has_rare_terms;          // a PAIR_SUM / ANGLE boundary exists (their sums go through shared memory)
+    int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 2 the hand-off kernel stores optimistically; bit 3 the LOCAL kernel
+                                 // releases the next launch right after its own wait instead of after its loads; bit 4 the LOCAL
+                                 // kernel's slot warps load with plain L1-bypassing loads instead of L2 evict_last hints
 };
+constexpr int kLayoutAligned = 0, kLayoutPacked = 1;
+constexpr int kTuneHandoffOptimistic = 4, kTuneReleaseFirst = 8, kTunePlainSlotLoads = 16;
+constexpr int kMaxPackedGroups = 4;
 
 // shared-memory scratch of the CV phase
 struct CvShared {
@@ -119,6 +132,13 @@ __device__ __forceinline__ void cv_accumulate(CvShared& sh, bool valid, int g, d
     }
 }
 
+// one slot's contribution to its group's fixed-point centroid sums
+__device__ __forceinline__ void cv_fixed(double w, double px, double py, double pz, long long& qx, long long& qy, long long& qz) {
+    qx = __double2ll_rn(__dmul_rn(__dmul_rn(w, px), kFixedScale));
+    qy = __double2ll_rn(__dmul_rn(__dmul_rn(w, py), kFixedScale));
+    qz = __double2ll_rn(__dmul_rn(__dmul_rn(w, pz), kFixedScale));
+}
+
 // cv_accumulate() for callers that know the host's slot layout holds (every group padded to whole warps, so the 32 lanes
 // of a warp always belong to one group): no votes, straight to the REDUX sums
 __device__ __forceinline__ void cv_accumulate_aligned(CvShared& sh, int g, double w, double px, double py, double pz) {
@@ -136,17 +156,6 @@ __device__ __forceinline__ void cv_accumulate_aligned(CvShared& sh, int g, doubl
             atomicAdd((unsigned long long*) &sh.acc[gi * 3 + 2], (unsigned long long) qz);
         }
     }
-}
-
-__device__ __forceinline__ double cv_centroid(const CvShared& sh, int g, int c) {
-    return __dmul_rn(__ll2double_rn(sh.acc[g * 3 + c]), kFixedInvScale);
-}
-
-__device__ __forceinline__ double cv_sqdist(const CvShared& sh, int ga, int gb) {
-    const double d0 = __dsub_rn(cv_centroid(sh, ga, 0), cv_centroid(sh, gb, 0));
-    const double d1 = __dsub_rn(cv_centroid(sh, ga, 1), cv_centroid(sh, gb, 1));
-    const double d2 = __dsub_rn(cv_centroid(sh, ga, 2), cv_centroid(sh, gb, 2));
-    return __fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0)));
 }
 
 // the two rarer forms of the examples (demo4 pair-sum, demo5 angle): kept out of line so that the common path
@@ -177,55 +186,41 @@ __device__ __noinline__ double cv_term_rare(const long long* acc, const Boundary
     return __dsub_rn(__dmul_rn(b.center[0], __dsqrt_rn(__dmul_rn(na2, nb2))), dot);   // center[0] = cos(ref)
 }
 
-// one boundary term; evaluated by lane b of warp 0 after the accumulators are complete.  Sphere (pair or fixed
-// centre) and plane -- what MMVT anchors are made of -- are computed without a branch and selected.
-__device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b) {
-    double u;
-    if (b.type > SEEKR2_B200_CV_PLANE) {
-        u = cv_term_rare(sh.acc, &b);
-    } else {
-        const int ga = b.groups[0], gb = b.groups[1];     // groups[1] is a valid index (0) when unused
-        const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
-        const double ax = cv_centroid(sh, ga, 0), ay = cv_centroid(sh, ga, 1), az = cv_centroid(sh, ga, 2);
-        const double bx = pair ? cv_centroid(sh, gb, 0) : b.center[0];
-        const double by = pair ? cv_centroid(sh, gb, 1) : b.center[1];
-        const double bz = pair ? cv_centroid(sh, gb, 2) : b.center[2];
-        const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
-        const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
-        const double u_sphere = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
-        const double along = b.axis == 0 ? ax : (b.axis == 1 ? ay : az);
-        const double u_plane = __dsub_rn(along, b.threshold);
-        u = b.type == SEEKR2_B200_CV_PLANE ? u_plane : u_sphere;
-    }
+__device__ __forceinline__ double fixed_to_nm(long long a) { return __dmul_rn(__ll2double_rn(a), kFixedInvScale); }
+
+// Surface function u of the common forms -- sphere (pair or fixed centre) and plane, what MMVT anchors are made of -- from
+// the fixed-point centroid sums of the boundary's first two groups, held in registers; computed without a branch and selected.
+__device__ __forceinline__ double cv_u_common(const Boundary& b, long long a0, long long a1, long long a2,
+                                              long long b0, long long b1, long long b2) {
+    const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
+    const double ax = fixed_to_nm(a0), ay = fixed_to_nm(a1), az = fixed_to_nm(a2);
+    const double bx = pair ? fixed_to_nm(b0) : b.center[0];
+    const double by = pair ? fixed_to_nm(b1) : b.center[1];
+    const double bz = pair ? fixed_to_nm(b2) : b.center[2];
+    const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+    const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+    const double u_sphere = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
+    const double along = b.axis == 0 ? ax : (b.axis == 1 ? ay : az);
+    const double u_plane = __dsub_rn(along, b.threshold);
+    return b.type == SEEKR2_B200_CV_PLANE ? u_plane : u_sphere;
+}
+
+// term contributed to the force-group energy: bitcode * step(k u) (step(0) = 1), or k u for the older non-step() style
+__device__ __forceinline__ double cv_term_of(const Boundary& b, double u) {
     const double ku = __dmul_rn(b.k, u);
     if (b.style == SEEKR2_B200_STYLE_RAW) return ku;
     return ku >= 0.0 ? b.bitcode : 0.0;
 }
 
-// cv_term() for a boundary held in REGISTERS (b is a by-value copy whose fields are only accessed with static indices;
-// the rare forms index groups[] dynamically and therefore go through b_mem, the same boundary in memory)
+// one boundary term; evaluated by lane b of warp 0 after the accumulators in shared memory are complete.  b_mem is the same
+// boundary in memory (the rare forms index groups[] dynamically; b itself may live in registers: only static indices below).
 __device__ __forceinline__ double cv_term_regs(const CvShared& sh, const Boundary& b, const Boundary* b_mem) {
-    double u;
-    if (b.type > SEEKR2_B200_CV_PLANE) {
-        u = cv_term_rare(sh.acc, b_mem);
-    } else {
-        const int ga = b.groups[0], gb = b.groups[1];
-        const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
-        const double ax = cv_centroid(sh, ga, 0), ay = cv_centroid(sh, ga, 1), az = cv_centroid(sh, ga, 2);
-        const double bx = pair ? cv_centroid(sh, gb, 0) : b.center[0];
-        const double by = pair ? cv_centroid(sh, gb, 1) : b.center[1];
-        const double bz = pair ? cv_centroid(sh, gb, 2) : b.center[2];
-        const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
-        const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
-        const double u_sphere = __dsub_rn(d2, __dmul_rn(b.threshold, b.threshold));
-        const double along = b.axis == 0 ? ax : (b.axis == 1 ? ay : az);
-        const double u_plane = __dsub_rn(along, b.threshold);
-        u = b.type == SEEKR2_B200_CV_PLANE ? u_plane : u_sphere;
-    }
-    const double ku = __dmul_rn(b.k, u);
-    if (b.style == SEEKR2_B200_STYLE_RAW) return ku;
-    return ku >= 0.0 ? b.bitcode : 0.0;
+    if (b.type > SEEKR2_B200_CV_PLANE) return cv_term_of(b, cv_term_rare(sh.acc, b_mem));
+    const int ga = b.groups[0], gb = b.groups[1];         // groups[1] is a valid index (0) when unused
+    return cv_term_of(b, cv_u_common(b, sh.acc[ga * 3], sh.acc[ga * 3 + 1], sh.acc[ga * 3 + 2],
+                                     sh.acc[gb * 3], sh.acc[gb * 3 + 1], sh.acc[gb * 3 + 2]));
 }
+__device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b) { return cv_term_regs(sh, b, &b); }
 
 // warp 0: lane b evaluates boundary b of this anchor into shared memory
 __device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, const Boundary& b, int lane = threadIdx.x) {

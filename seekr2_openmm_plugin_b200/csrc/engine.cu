@@ -74,6 +74,12 @@ struct seekr2_b200_engine {
     bool slab_valid = false;
     bool use_pdl = true;            // fused step kernels are launched with programmatic stream serialization (SEEKR2_B200_PDL=0: off)
     bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
+    int local_grid_x = 0;           // LOCAL mode: blocks per anchor (0 = not sized yet; sized at the first launch from the occupancy of the
+                                    // instantiation that runs, so that the whole grid is resident at once)
+    int sm_count = 0;
+    bool plain_next = true;         // the next fused launch is an ordinary one (no programmatic dependent launch): set whenever the step-index
+                                    // shadow was (re)written by something other than the fused launch two steps back
+    bool shadow_stale = false;      // two-pass steps advanced the clock but not the step-index shadow
     // device allocations
     int* d_slot_atom = nullptr;
     int* d_slot_group = nullptr;
@@ -95,6 +101,7 @@ struct seekr2_b200_engine {
     long long* d_pack_scratch = nullptr;      // [3 A]
     Record* h_stage = nullptr;                // [kStageRecords], written by ring_pack_kernel over PCIe
     long long* h_stage_hdr = nullptr;         // [4]
+    long long* h_stage_clock = nullptr;       // [A][2] time bits, step count of every anchor as of the last drain
     cudaEvent_t drain_event = nullptr;
     bool drain_pending = false;
     // graph capture
@@ -102,6 +109,7 @@ struct seekr2_b200_engine {
     cudaGraphExec_t graph_exec = nullptr;
     bool capturing = false;
     int capture_phase0 = 0;
+    bool capture_plain0 = true;
     int capture_steps = 0;
     int graph_steps = 0;
 };
@@ -164,19 +172,32 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
 
 template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
     const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
+    const bool pdl = h->use_pdl && !h->plain_next;
     if (h->local_decide) {
-        // kThreads streaming threads + one thread per (warp-padded) boundary-group slot
-        const unsigned threads = kThreads + (KIND == SEEKR2_B200_KIND_LANGEVIN ? 0u : (unsigned) ((h->dev.num_slots > 0 ? h->dev.num_slots + 31 : 32) & ~31));
+        // T streaming threads + the slot warps (none for plain Langevin)
+        const int T = h->dev.local_stream_threads;
+        const unsigned threads = (unsigned) T + (KIND == SEEKR2_B200_KIND_LANGEVIN ? 0u : (unsigned) h->dev.slot_threads);
+        if (h->local_grid_x == 0) {
+            // blocks per anchor: as many as are resident at once (each then walks ceil(tiles / G) tiles)
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_local_kernel<P, KIND, SCHEME>, (int) threads, 0));
+            long long resident = (long long) (per_sm > 0 ? per_sm : 1) * h->sm_count;
+            if (const char* g = getenv("SEEKR2_B200_LOCAL_RESIDENT")) resident = atoll(g);                          // tuning knob
+            long long gx = resident / h->cfg.num_anchors;
+            if (gx < 1) gx = 1;
+            if (gx > h->dev.local_tiles) gx = h->dev.local_tiles;
+            h->local_grid_x = (int) gx;
+        }
         // programmatic dependent launch: the next step's blocks may start their (static) prologue under this launch's body
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned) bpa, (unsigned) h->cfg.num_anchors, 1);
+        lc.gridDim = dim3((unsigned) h->local_grid_x, (unsigned) h->cfg.num_anchors, 1);
         lc.blockDim = dim3(threads, 1, 1);
         lc.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = attr;
-        lc.numAttrs = h->use_pdl ? 1 : 0;
+        lc.numAttrs = pdl ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase));
         return SEEKR2_B200_OK;
     }
@@ -189,7 +210,7 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = h->use_pdl ? 1 : 0;
+    lc.numAttrs = pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase, bpa));
     return SEEKR2_B200_OK;
 }
@@ -272,6 +293,7 @@ int seekr2_b200_destroy(seekr2_b200_handle h) {
     cudaFree(h->d_ring_tail); cudaFree(h->d_pack_scratch);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_stage_hdr) cudaFreeHost(h->h_stage_hdr);
+    if (h->h_stage_clock) cudaFreeHost(h->h_stage_clock);
     if (h->drain_event) cudaEventDestroy(h->drain_event);
     delete h;
     return SEEKR2_B200_OK;
@@ -294,36 +316,22 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     if (cfg->num_groups > 0 && (!cfg->group_offsets || !cfg->group_atoms || !cfg->group_weights)) return fail(SEEKR2_B200_ERR_INVALID, "group arrays missing");
     if (cfg->num_boundaries > 0 && !cfg->boundaries) return fail(SEEKR2_B200_ERR_INVALID, "boundary array missing");
 
-    // Group slots, padded so that every warp of a decide block holds slots of ONE group only: each
-    // group's slot range is rounded up to a multiple of 32 with weight-0 copies of its last atom.
-    // The warp-level reduction of the centroid sums then never mixes groups (no per-lane atomics).
-    std::vector<int> slot_atom, slot_group;
-    std::vector<double> slot_weight;
+    // centroid groups: OpenMM normalises the weights of a group so that they sum to one
+    std::vector<double> norm_weight;
+    int real_slots = 0, aligned_slots = 0;
     for (int g = 0; g < cfg->num_groups; g++) {
         const int lo = cfg->group_offsets[g], hi = cfg->group_offsets[g + 1];
         if (hi <= lo) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d is empty", g);
-        // OpenMM normalises the weights of a centroid group so that they sum to one
         double sum = 0.0;
         for (int j = lo; j < hi; j++) sum += cfg->group_weights[j];
         if (!(sum > 0.0)) return fail(SEEKR2_B200_ERR_INVALID, "centroid group %d has non-positive total weight", g);
         for (int j = lo; j < hi; j++) {
             if (cfg->group_atoms[j] < 0 || cfg->group_atoms[j] >= cfg->num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "group %d references atom %d outside [0,%d)", g, cfg->group_atoms[j], cfg->num_atoms);
-            slot_atom.push_back(cfg->group_atoms[j]);
-            slot_group.push_back(g);
-            slot_weight.push_back(cfg->group_weights[j] / sum);
+            norm_weight.push_back(cfg->group_weights[j] / sum);
         }
-        const size_t first = slot_atom.size() - (size_t) (hi - lo);
-        while (slot_atom.size() % 32 != 0) {
-            slot_atom.push_back(cfg->group_atoms[hi - 1]);
-            slot_group.push_back(g);
-            slot_weight.push_back(0.0);
-        }
-        // a group that fits into one warp's 32 slots is summed by that warp alone: its leader stores the sums
-        // instead of adding them atomically (cv_accumulate)
-        if (slot_atom.size() - first == 32)
-            for (size_t j = first; j < slot_atom.size(); j++) slot_group[j] |= kGroupSingleWarp;
+        real_slots += hi - lo;
+        aligned_slots += (hi - lo + 31) & ~31;
     }
-    const int num_slots = (int) slot_atom.size();
     for (int a = 0; a < cfg->num_anchors; a++)
         for (int i = 0; i < cfg->num_boundaries; i++) {
             const seekr2_b200_boundary& bd = cfg->boundaries[(size_t) a * cfg->num_boundaries + i];
@@ -360,6 +368,78 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
 
     const int A = cfg->num_anchors;
     EngineDev& d = h->dev;
+    auto bail = [&](int code) { seekr2_b200_destroy(h); return code; };
+    cudaDeviceProp prop;
+    {
+        const cudaError_t perr = cudaGetDeviceProperties(&prop, h->device);
+        if (perr != cudaSuccess) return bail(fail(SEEKR2_B200_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(perr)));
+    }
+    h->sm_count = prop.multiProcessorCount;
+    const int snap_slots = cfg->save_state_slots > 0 ? cfg->save_state_slots : 0;
+
+    // Decision mode of the fused step.  LOCAL (every block evaluates the boundaries itself in its own slot warps, optimistic
+    // stores, no hand-off through global memory) is for launches whose state lives in L2 -- one to a few tens of anchors per
+    // GPU, bound by latency and instruction issue; the decide-block hand-off is for batched, HBM-bound launches, where the
+    // redundant slot warps and the larger register budget would cost bandwidth.
+    bool local;
+    {
+        const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
+        const bool eligible = snap_slots == 0 && aligned_slots <= kThreads;
+        long long limit = (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
+        if (const char* lm = getenv("SEEKR2_B200_LOCAL_LIMIT")) limit = atoll(lm);                                   // tuning knob
+        local = eligible && stream_blocks <= limit;
+        if (const char* m = getenv("SEEKR2_B200_DECIDE")) {                                                         // A/B knob
+            if (m[0] == 'l') local = eligible;
+            if (m[0] == 'h') local = false;
+        }
+        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_HANDOFF) local = false;
+        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_LOCAL) {
+            if (!eligible) return bail(fail(SEEKR2_B200_ERR_INVALID, "FLAG_DECIDE_LOCAL needs save_state_slots == 0 and at most %d group slots (have %d)", kThreads, aligned_slots));
+            local = true;
+        }
+        h->local_decide = local;
+        if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
+    }
+
+    // Group slots.  ALIGNED layout (hand-off kernel; LOCAL with larger groups): every group's slot range is rounded up to a
+    // multiple of 32 with weight-0 copies of its last atom, so that each warp holds slots of ONE group only and the warp-level
+    // reduction of the centroid sums never mixes groups.  PACKED layout (LOCAL mode, all group atoms together fit one warp):
+    // the groups sit side by side in a single warp and are summed with masked reductions in registers.
+    bool packed = local && real_slots <= 32 && cfg->num_groups <= kMaxPackedGroups;
+    if (const char* pk = getenv("SEEKR2_B200_PACKED")) if (pk[0] == '0') packed = false;                            // A/B knob
+    std::vector<int> slot_atom, slot_group;
+    std::vector<double> slot_weight;
+    for (int g = 0, nw = 0; g < cfg->num_groups; g++) {
+        const int lo = cfg->group_offsets[g], hi = cfg->group_offsets[g + 1];
+        const size_t first = slot_atom.size();
+        for (int j = lo; j < hi; j++) {
+            slot_atom.push_back(cfg->group_atoms[j]);
+            slot_group.push_back(g);
+            slot_weight.push_back(norm_weight[nw++]);
+        }
+        if (packed) continue;
+        while (slot_atom.size() % 32 != 0) {
+            slot_atom.push_back(cfg->group_atoms[hi - 1]);
+            slot_group.push_back(g);
+            slot_weight.push_back(0.0);
+        }
+        // a group that fits into one warp's 32 slots is summed by that warp alone: its leader stores the sums
+        // instead of adding them atomically (cv_accumulate)
+        if (slot_atom.size() - first == 32)
+            for (size_t j = first; j < slot_atom.size(); j++) slot_group[j] |= kGroupSingleWarp;
+    }
+    const int num_slots = (int) slot_atom.size();
+    d.slot_layout = (packed || num_slots == 0) ? kLayoutPacked : kLayoutAligned;
+    d.slot_threads = d.slot_layout == kLayoutPacked ? 32 : num_slots;
+    {
+        int T = kThreads;
+        if (const char* lt = getenv("SEEKR2_B200_LOCAL_THREADS")) T = atoi(lt);                                      // tuning knob
+        if (T < 32 || T > 512 || (T & 31)) return bail(fail(SEEKR2_B200_ERR_INVALID, "SEEKR2_B200_LOCAL_THREADS must be a multiple of 32 in [32, 512]"));
+        d.local_stream_threads = T;
+        d.local_tiles = (cfg->num_atoms + T - 1) / T;
+    }
+    d.tune = 0;
+    if (const char* tn = getenv("SEEKR2_B200_TUNE")) d.tune = atoi(tn);                                             // tuning knob
     d.num_atoms = cfg->num_atoms; d.padded_num_atoms = cfg->padded_num_atoms; d.num_anchors = A;
     d.num_slots = num_slots; d.num_groups = cfg->num_groups; d.num_boundaries = cfg->num_boundaries;
     d.num_milestone_groups = cfg->num_milestone_groups;
@@ -369,7 +449,6 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     for (int i = 0; i < cfg->num_dest; i++) d.dest_groups[i] = cfg->dest_groups[i];
     d.ring_capacity = h->cfg.ring_capacity;
 
-    auto bail = [&](int code) { seekr2_b200_destroy(h); return code; };
 #define CREATE_TRY(call)                                                                            \
     do {                                                                                            \
         cudaError_t err__ = (call);                                                                 \
@@ -398,9 +477,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         CREATE_TRY(cudaMemcpy(h->d_boundaries, bounds.data(), sizeof(Boundary) * nb, cudaMemcpyHostToDevice));
     }
     d.mmvt_any_term = 1;
+    d.has_rare_terms = 0;
     for (size_t i = 0; i < (size_t) A * cfg->num_boundaries; i++) {
         const Boundary& bd = cfg->boundaries[i];
         if (bd.force_group == 1 && !(bd.style == SEEKR2_B200_STYLE_STEP && bd.bitcode >= 1.0 && bd.bitcode <= 2147483648.0)) d.mmvt_any_term = 0;
+        if (bd.type > SEEKR2_B200_CV_PLANE) d.has_rare_terms = 1;
     }
     CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
@@ -429,13 +510,15 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     CREATE_TRY(cudaHostAlloc(&h->h_stage, sizeof(Record) * kStageRecords, cudaHostAllocMapped));
     CREATE_TRY(cudaHostAlloc(&h->h_stage_hdr, sizeof(long long) * 4, cudaHostAllocMapped));
     memset(h->h_stage_hdr, 0, sizeof(long long) * 4);
+    CREATE_TRY(cudaHostAlloc(&h->h_stage_clock, sizeof(long long) * 2 * A, cudaHostAllocMapped));
+    memset(h->h_stage_clock, 0, sizeof(long long) * 2 * A);
     CREATE_TRY(cudaEventCreateWithFlags(&h->drain_event, cudaEventDisableTiming));
 
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
     d.decision = h->d_decision; d.flags = h->d_flags; d.step_shadow = h->d_step_shadow;
     d.rng_seed = 0; d.rng_anchor_base = 0; d.probe = nullptr;
-    d.snap_slots = cfg->save_state_slots > 0 ? cfg->save_state_slots : 0;
+    d.snap_slots = snap_slots;
     if (d.snap_slots > 0) {
         if (d.snap_slots >= (1 << 20)) return bail(fail(SEEKR2_B200_ERR_INVALID, "too many save_state_slots"));
         const size_t per = (size_t) A * d.snap_slots * cfg->padded_num_atoms;
@@ -447,8 +530,6 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.snap_posq = h->d_snap_posq; d.snap_corr = h->d_snap_corr; d.snap_velm = h->d_snap_velm;
     d.head_start = h->d_flags + 2 * A;
     {
-        cudaDeviceProp prop;
-        CREATE_TRY(cudaGetDeviceProperties(&prop, h->device));
         // streaming blocks resident when the kernel starts: SMs x blocks per SM, minus the decide blocks
         d.first_wave_blocks = prop.multiProcessorCount * kFusedMinBlocks - A;
         if (d.first_wave_blocks < 0) d.first_wave_blocks = 0;
@@ -457,23 +538,6 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         d.head_start_target = A * slot_warps;
         d.prefetch_ahead = d.first_wave_blocks;
         if (const char* pf = getenv("SEEKR2_B200_PREFETCH")) if (pf[0] == '0') d.prefetch_ahead = 0;               // tuning knob
-        // Decision mode of the fused step.  LOCAL (every block evaluates the boundaries itself, no hand-off) is for the
-        // latency-bound regime: the whole launch resident at once with room to spare; the decide-block hand-off is for
-        // batched, HBM-bound launches, where redundant group gathers and 2x the registers would cost bandwidth.
-        const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
-        const bool eligible = d.snap_slots == 0 && num_slots <= kThreads;
-        bool local = eligible && stream_blocks <= (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
-        if (const char* m = getenv("SEEKR2_B200_DECIDE")) {                                                         // A/B knob
-            if (m[0] == 'l') local = eligible;
-            if (m[0] == 'h') local = false;
-        }
-        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_HANDOFF) local = false;
-        if (cfg->flags & SEEKR2_B200_FLAG_DECIDE_LOCAL) {
-            if (!eligible) return bail(fail(SEEKR2_B200_ERR_INVALID, "FLAG_DECIDE_LOCAL needs save_state_slots == 0 and at most %d group slots (have %d)", kThreads, num_slots));
-            local = true;
-        }
-        h->local_decide = local;
-        if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                   // A/B knob
     }
     *out = h;
     return SEEKR2_B200_OK;
@@ -522,7 +586,11 @@ int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* buf
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
     int rc = DISPATCH_PRECISION(h, launch_gather<SINGLE>(h, bufs, s), launch_gather<MIXED>(h, bufs, s), launch_gather<DOUBLE>(h, bufs, s));
-    if (rc == SEEKR2_B200_OK) h->slab_valid = true;
+    if (rc == SEEKR2_B200_OK) {
+        h->slab_valid = true;
+        h->shadow_stale = false;     // launch_gather ends with refresh_shadow_kernel
+        h->plain_next = true;        // ... an ordinary launch: the next fused launch must not read the shadow before it has completed
+    }
     return rc;
 }
 
@@ -550,11 +618,20 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
         return fail(SEEKR2_B200_ERR_INVALID, "seekr2_b200_sync_groups must be called before the first fused step");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
+    if (h->shadow_stale) {
+        // two-pass steps advanced the clock but not the step-index shadow the fused kernels read (every kind, with or without slots)
+        if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "a fused step after two-pass steps cannot be the first thing captured: call seekr2_b200_sync_groups before seekr2_b200_graph_begin");
+        refresh_shadow_kernel<<<(h->cfg.num_anchors + 127) / 128, 128, 0, s>>>(h->dev, h->phase);
+        CUDA_TRY(cudaGetLastError());
+        h->shadow_stale = false;
+        h->plain_next = true;
+    }
     int rc = DISPATCH_PRECISION(h, launch_fused_kind<SINGLE>(h, bufs, random_index, s),
                                 launch_fused_kind<MIXED>(h, bufs, random_index, s),
                                 launch_fused_kind<DOUBLE>(h, bufs, random_index, s));
     if (rc != SEEKR2_B200_OK) return rc;
     h->phase = (h->phase + 1) & 3;   // slab half and decision flag alternate every launch; the step-index slots cycle through four
+    h->plain_next = false;
     if (h->capturing) h->capture_steps++;
     return SEEKR2_B200_OK;
 }
@@ -587,7 +664,8 @@ int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, vo
         return fail(SEEKR2_B200_ERR_INVALID, "the MIDDLE multi-pass path needs d_old_delta (and d_old_velm for MMVT)");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t) stream;
-    h->slab_valid = false;   // the two-pass path does not maintain the slab
+    h->slab_valid = false;   // the two-pass path does not maintain the slab ...
+    h->shadow_stale = true;  // ... nor the step-index shadow of the fused kernels
     return DISPATCH_PRECISION(h, launch_finish_kind<SINGLE>(h, bufs, s), launch_finish_kind<MIXED>(h, bufs, s),
                               launch_finish_kind<DOUBLE>(h, bufs, s));
 }
@@ -602,6 +680,8 @@ int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
     h->capturing = true;
     h->capture_phase0 = h->phase;
     h->capture_steps = 0;
+    h->capture_plain0 = h->plain_next;
+    h->plain_next = true;            // the graph's first step has no kernel of this graph in front of it
     return SEEKR2_B200_OK;
 }
 
@@ -613,6 +693,7 @@ int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream) {
     CUDA_TRY(cudaStreamEndCapture((cudaStream_t) stream, &g));
     h->graph = g;
     h->phase = h->capture_phase0;        // the captured steps have not run yet
+    h->plain_next = h->capture_plain0;
     h->graph_steps = h->capture_steps;
     if (h->graph_steps & 3)
         return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain a multiple of 4 fused steps (the launch phase is baked into each launch); got %d", h->graph_steps);
@@ -625,6 +706,7 @@ int seekr2_b200_graph_launch(seekr2_b200_handle h, void* stream) {
     if (h->phase != h->capture_phase0) return fail(SEEKR2_B200_ERR_INVALID, "launch phase differs from the one the graph was captured with");
     DeviceGuard guard(h->device);
     CUDA_TRY(cudaGraphLaunch(h->graph_exec, (cudaStream_t) stream));
+    h->plain_next = false;
     return SEEKR2_B200_OK;
 }
 
@@ -640,10 +722,12 @@ int seekr2_b200_drain_begin(seekr2_b200_handle h, int64_t max_records, void* str
     cudaStream_t s = (cudaStream_t) stream;
     Record* d_stage = nullptr;
     long long* d_hdr = nullptr;
+    long long* d_clock = nullptr;
     CUDA_TRY(cudaHostGetDevicePointer((void**) &d_stage, h->h_stage, 0));
     CUDA_TRY(cudaHostGetDevicePointer((void**) &d_hdr, h->h_stage_hdr, 0));
+    CUDA_TRY(cudaHostGetDevicePointer((void**) &d_clock, h->h_stage_clock, 0));
     const long long limit = max_records < kStageRecords ? max_records : kStageRecords;
-    ring_pack_kernel<<<1, 1024, 0, s>>>(h->dev, h->d_ring_tail, h->d_pack_scratch, d_stage, d_hdr, limit);
+    ring_pack_kernel<<<1, 1024, 0, s>>>(h->dev, h->d_ring_tail, h->d_pack_scratch, d_stage, d_hdr, d_clock, limit);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->drain_event, s));
     h->drain_pending = true;
@@ -666,6 +750,14 @@ int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t
     }
     *out_n = n;
     if (h->h_stage_hdr[1]) return fail(SEEKR2_B200_ERR_RING_OVERFLOW, "crossing ring overflowed: records were lost; drain more often or raise ring_capacity");
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_drain_clock(seekr2_b200_handle h, int32_t anchor, double* time, int64_t* step_count) {
+    if (!h || anchor < 0 || anchor >= h->cfg.num_anchors) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    if (h->drain_pending) return fail(SEEKR2_B200_ERR_INVALID, "a drain is in flight: call seekr2_b200_drain_end first");
+    if (time) memcpy(time, &h->h_stage_clock[2 * anchor], sizeof(double));
+    if (step_count) *step_count = h->h_stage_clock[2 * anchor + 1];
     return SEEKR2_B200_OK;
 }
 
@@ -699,15 +791,12 @@ int seekr2_b200_get_state(seekr2_b200_handle h, int32_t anchor, seekr2_b200_anch
 
 int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int64_t step_count, void* stream) {
     if (!h || anchor < 0 || anchor >= h->cfg.num_anchors) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "set_time cannot be captured");
     DeviceGuard guard(h->device);
-    cudaStream_t s = (cudaStream_t) stream;
-    CUDA_TRY(cudaStreamSynchronize(s));
-    CUDA_TRY(cudaMemcpy(&h->d_state[anchor].time, &time, sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(&h->d_state[anchor].step_count, &step_count, sizeof(int64_t), cudaMemcpyHostToDevice));
-    for (int ahead = 0; ahead < 2; ahead++) {       // the next launch reads slot `phase`, the one after it slot `phase + 1`
-        const int64_t v = step_count + ahead;
-        CUDA_TRY(cudaMemcpy(&h->d_step_shadow[((h->phase + ahead) & 3) * h->cfg.num_anchors + anchor], &v, sizeof(int64_t), cudaMemcpyHostToDevice));
-    }
+    // one tiny launch carrying the values as kernel parameters: stream-ordered, no host synchronisation, no staging buffer
+    set_time_kernel<<<1, 1, 0, (cudaStream_t) stream>>>(h->dev, anchor, time, (long long) step_count, h->phase);
+    CUDA_TRY(cudaGetLastError());
+    h->plain_next = true;            // the step-index shadow was written by an ordinary launch
     return SEEKR2_B200_OK;
 }
 

@@ -136,3 +136,57 @@ def test_long_run_local_equals_handoff(cuda_device):
     assert all(c == (cl[0][0], steps) for c in cl)
     for a in range(A):
         H.assert_state_equal(gl[a], gh[a], n, f"local vs handoff after {steps} steps, anchor {a}")
+
+
+KNOB_SETS = [
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "128"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6"},      # one block per anchor walks every tile
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "96", "SEEKR2_B200_LOCAL_RESIDENT": "20", "SEEKR2_B200_TUNE": "3"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_TUNE": "3"},                                                # normals before griddepcontrol.wait
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PACKED": "0"},                                              # aligned layout for one-warp groups
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PDL": "0"},
+    {"SEEKR2_B200_DECIDE": "h", "SEEKR2_B200_TUNE": "4"},                                                # hand-off kernel, optimistic stores
+]
+
+
+@pytest.mark.parametrize("kind,middle,variant,restore", [("mmvt", False, "cuda", False), ("mmvt", True, "cuda", True),
+                                                         ("mmvt", False, "reference", True), ("elber", False, "cuda", False)])
+def test_kernel_knobs_do_not_change_a_bit(cuda_device, monkeypatch, kind, middle, variant, restore):
+    """The LOCAL kernel's launch shape (streaming threads per block, tiles per block), the packed / aligned slot layout, early
+    normals, programmatic dependent launch and the hand-off kernel's optimistic stores are tuning knobs: every setting must
+    give the bits of the default hand-off kernel (which the other modules pin to the oracle) -- atoms, records, statistics,
+    clock -- on 4 anchors x 3 000 atoms over 400 steps with bounces, under 8-step graph replay."""
+    A, n = 4, 3000
+
+    def run(env):
+        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        syn, positions = _shell_workload(A, n, H.SEED_BASE + 65)
+        if kind == "mmvt":
+            integ = H.make_mmvt_integrator(syn, "", variant=variant, middle=middle)
+        else:
+            integ = s2.ElberLangevinIntegrator(syn.temperature, syn.friction, syn.dt, "")
+            integ.addSrcMilestoneGroup(1)
+            integ.setEndOnSrcMilestone(False)
+        integ.setRestoreCorrection(restore)
+        integ.setRandomNumberSeed(13)
+        integ.setUseGraph(True, 8)
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
+        assert integ.getDecisionMode() == ("local" if env.get("SEEKR2_B200_DECIDE") == "l" else "handoff")
+        ctx.setPositions(positions)
+        ctx.setVelocities(syn.velocities)
+        integ.step(400)
+        return ([H.download(ctx, a) for a in range(A)], [H.records_as_tuples(integ.getRecords(a)) for a in range(A)],
+                [H.stats_tuple(integ.getAnchorState(a), 2) for a in range(A)],
+                [(integ.getAnchorState(a).time, integ.getAnchorState(a).step_count) for a in range(A)])
+
+    ref = run({"SEEKR2_B200_DECIDE": "h"})
+    if kind == "mmvt":
+        assert sum(len(r) for r in ref[1]) >= 4, "the run must bounce"
+    for env in KNOB_SETS:
+        got = run(env)
+        assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3], env
+        for a in range(A):
+            H.assert_state_equal(ref[0][a], got[0][a], n, f"{env}, anchor {a}")

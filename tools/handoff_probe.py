@@ -1,4 +1,6 @@
-"""Measures the decide -> streaming hand-off inside fused_step_kernel with the debug probe."""
+"""Measures the decide -> streaming hand-off inside the fused kernels with the debug probe.  Needs the probe build:
+    make -C seekr2_openmm_plugin_b200/csrc probe
+    SEEKR2_B200_LIBRARY=seekr2_openmm_plugin_b200/libseekr2_b200_probe.so python tools/handoff_probe.py 1 23036 local"""
 import ctypes as C, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,11 +34,12 @@ for it in range(3):
           f"(mean {p[8*A+2]/max(1,p[8*A]):.0f} ns per waiting block)")
     cyc = p[8 * A + 4: 8 * A + 4 + 11]
     if integ.getDecisionMode() == "local":
-        stages = ["round 1 issued", "force gather issued (index back)", "normals done", "slot atom advanced", "own atom advanced",
-                  "sums reduced (slot-warp barrier)", "boundary terms", "decision (streaming: barrier passed)", "own stores issued", "slab write-back issued"]
-        for who, off in (("block 0, slot thread 0 (leader)", 0), ("block 1, streaming thread 128", 16)):
+        slot = ["wait returned", "gathers issued", "slot atom advanced", "sums reduced", "terms evaluated", "published (arrived)", "slab + clock done"]
+        strm = ["wait returned", "loads issued", "", "own atom advanced", "optimistic stores issued", "barrier passed", "end"]
+        for who, off, stages in (("block 0, slot thread 0 (leader)", 0, slot), ("last block, streaming thread T/2", 16, strm)):
             c = p[8 * A + 4 + off: 8 * A + 4 + off + 11]
-            print(f"   LOCAL mode, {who}, SM cycles since block start: " + "; ".join(f"{n} {int(c[i + 1] - c[0])}" for i, n in enumerate(stages) if c[i + 1] > 0))
+            print(f"   LOCAL mode, {who}, SM cycles since block start: " + "; ".join(f"{n} {int(c[i + 1] - c[0])}" for i, n in enumerate(stages) if c[i + 1] > 0)
+                  + (f"; [loads returned {int(c[8] - c[0])}]" if c[8] > 0 else ""))
         continue
     stages = ["step index loaded", "gathers issued", "gathers back", "cleared+sync", "advanced", "accumulated", "all warps reduced",
               "boundary terms", "published", "bookkeeping+slab+clock"]
