@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SEEKR2_B200_ABI_VERSION 8
+#define SEEKR2_B200_ABI_VERSION 9
 
 #define SEEKR2_B200_MAX_MILESTONES 32   /* labels / bits tracked by the MMVT statistics          */
 #define SEEKR2_B200_MAX_BOUNDARIES 32   /* boundary terms per anchor                              */
@@ -230,7 +230,7 @@ typedef struct seekr2_b200_anchor_state {
     int32_t elber_sampled;       /* bit i set once milestone i has its baseline value              */
     float elber_values[SEEKR2_B200_MAX_ELBER]; /* src values then dest values                      */
     int32_t num_snapshots;       /* crossing states saved so far (save_state_slots > 0)            */
-    int32_t reserved0;
+    int32_t clock_resets;        /* Elber: times the step set the context time back to 0 (:545)     */
 } seekr2_b200_anchor_state;
 
 typedef struct seekr2_b200_engine* seekr2_b200_handle;
@@ -268,6 +268,20 @@ int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_bas
    anything else modified posq/velm (setPositions, setVelocities, reorderAtoms, a barostat).      */
 int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
 
+/* The light form of sync_groups for a caller that steps through seekr2_b200_step but cannot know whether something
+   else touched posq / velm since its last step (inside OpenMM: Context::setPositions / setVelocities, a barostat,
+   CMMotionRemover, atom reordering -- the reference is immune because it re-reads everything every step,
+   CudaSeekr2Kernels.cpp:214-246): ONE small launch that re-gathers the boundary-group atoms into the slab and takes the
+   step index from the anchor clock.  Queue it in front of every fused step; the pair is still a single pass over the
+   atoms (no posDelta round trip).  Not needed between back-to-back fused steps of a caller that owns the buffers.   */
+int seekr2_b200_resync(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
+
+/* OpenMM's CUDA platform reorders atoms now and then (cu.reorderAtoms(), CudaSeekr2Kernels.cpp:365): the buffers then
+   hold atom cu.getAtomIndex()[i] at index i.  index_of_atom[a] = current buffer index of the atom the config called `a`
+   ([num_atoms], host memory; the inverse of getAtomIndex()).  Remaps the group slots; stream-ordered behind the steps
+   already queued.  Follow with seekr2_b200_resync / sync_groups before the next fused step.                           */
+int seekr2_b200_set_atom_order(seekr2_b200_handle h, const int32_t* index_of_atom, void* stream);
+
 /* replaces the first-step test (CudaSeekr2Kernels.cpp:205-210): evaluates the MMVT boundary value
    at the current positions; returns SEEKR2_B200_ERR_FIRST_STEP if any anchor has value > 0 and
    writes per-anchor flags to out_flags[num_anchors] when non-NULL.  Synchronises the stream.     */
@@ -296,8 +310,10 @@ int seekr2_b200_kick(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
 int seekr2_b200_middle_drift(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint32_t random_index,
                              void* stream);
 /* replaces Part2 + calcForcesAndEnergy(false,true,mask) + the host crossing block + mmvtBounce
-   (CudaSeekr2Kernels.cpp:231-365 / :509-594): a one-block-per-anchor decision kernel followed by the
-   streaming finish with the bounce predicated on the device-side decision.                         */
+   (CudaSeekr2Kernels.cpp:231-365 / :509-594) in ONE launch: the grid's first num_anchors blocks evaluate the boundaries
+   at the pending positions (posq + posDelta) and hand the decision to the streaming blocks of the same launch, which
+   have loaded and drifted their atoms meanwhile and store with the bounce predicated on it.  A captured graph must
+   hold an even number of finish launches (the decision word alternates between two halves).        */
 int seekr2_b200_finish(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
 
 /* ---- CUDA graph of a sequence of steps -------------------------------------------------------- */
@@ -332,6 +348,13 @@ int seekr2_b200_drain_ready(seekr2_b200_handle h);
    after seekr2_b200_drain_end; reads host memory only, never blocks.  Lets the OpenMM adapter mirror Context time without a
    read-back per step.                                                                                              */
 int seekr2_b200_drain_clock(seekr2_b200_handle h, int32_t anchor, double* time, int64_t* step_count);
+/* What the device has reported so far WITHOUT any CUDA call: the step kernels mirror each anchor's ring head and (Elber)
+   the number of clock resets into mapped pinned host memory when they change, i.e. on crossing steps only.
+   *records_pending = records appended by steps that have already run, minus records handed out by drain_end;
+   *clock_resets = context-time resets so far (CudaSeekr2Kernels.cpp:545), summed over anchors.  Either may be NULL.
+   A hint (steps still queued have not reported yet): lets a one-step-per-call caller queue a drain only when there is
+   something to fetch instead of after every step.                                                              */
+int seekr2_b200_poll(seekr2_b200_handle h, int64_t* records_pending, int64_t* clock_resets);
 /* drain_begin + drain_end: blocks until everything queued on `stream` before the call has run.             */
 int seekr2_b200_drain(seekr2_b200_handle h, seekr2_b200_record* out, int64_t max_records,
                       int64_t* out_n, void* stream);

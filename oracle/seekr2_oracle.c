@@ -520,6 +520,7 @@ int seekr2_oracle_elber_step(seekr2_oracle* o, void* posq, void* corr, void* vel
                 } else {
                     o->st.crossed_src = 1;
                     o->st.time = 0.0;                                          /* context.setTime(0.0) :545 */
+                    o->st.clock_resets++;
                     o->srcValues[i] = value;
                 }
             }

@@ -21,6 +21,8 @@ struct B200BoundarySet {
 };
 /* throws OpenMM::OpenMMException for any CustomCentroidBondForce it cannot type */
 B200BoundarySet recogniseBoundaries(const OpenMM::System& system);
+/* throws if one of these force groups holds a Force that is not a CustomCentroidBondForce */
+void requireTypedMilestoneForces(const OpenMM::System& system, const std::vector<int>& forceGroups);
 
 class B200StepKernelBase {
 protected:
@@ -37,10 +39,19 @@ protected:
     void allocateScratch(bool oldVelm, bool oldDelta);
     OpenMM::CudaArray oldVelm, oldDelta;          /* multi-pass scratch (CudaSeekr2Kernels.cpp:618-643) */
     void drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc);
-    /* asynchronous drain (MMVT, SEEKR2_B200_ASYNC_DRAIN=1): execute() never waits for the device -- a drain is begun
-       behind each step's kernels and collected by a later execute() once it has landed; flushDrain() (blocking) runs
-       where the reference's files must be complete: computeKineticEnergy, statistics writes, destruction */
+    /* asynchronous drain (default; SEEKR2_B200_ASYNC_DRAIN=0 or a saveStateFileName turn it off): execute() never waits
+       for the device -- a drain is begun behind a step only when the device has reported something to fetch
+       (seekr2_b200_poll) and collected by a later execute() once it has landed; flushDrain() (blocking) runs where the
+       reference's files must be complete: computeKineticEnergy, destruction */
     bool asyncDrain = false, drainPending = false;
+    bool collected = false;          /* this execute() collected a drain (its clock is in the engine's staging area) */
+    bool clockValid = false, pendingClockValid = true;   /* ... and no set_time was issued after that drain was queued */
+    int64_t seenResets = 0;
+    int kind = 0;
+    bool fused = false;              /* one-launch step (no constraints, no virtual sites) */
+    std::vector<int32_t> slotIndex;  /* current buffer index of every boundary-group atom (cu.getAtomIndex()) */
+    void followAtomOrder();
+    bool deviceTime(long long stepsIssued, double stepSize, double& time);
     int64_t collectPending(bool block);           /* records handed to writeRecords(); -1 = not ready */
     void flushDrain();
     void writeRecords(int64_t n);
@@ -82,6 +93,8 @@ private:
     std::string outputFileName;
     std::vector<int32_t> labels;     /* source groups then destination groups */
     int numSrc = 0;
+    bool first = true;
+    double expectedTime = 0.0;       /* what cu.getTime() holds unless somebody called context.setTime() */
 };
 
 typedef B200MmvtStepKernel<IntegrateMmvtLangevinStepKernel, MmvtLangevinIntegrator, false> B200IntegrateMmvtLangevinStepKernel;

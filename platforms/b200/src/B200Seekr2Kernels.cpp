@@ -4,10 +4,18 @@
  *
  * Per step the reference does Part1 -> applyConstraints -> Part2 -> computeVirtualSites ->
  * calcForcesAndEnergy(false,true,mask) [blocking readback] -> host crossing block -> mmvtBounce.
- * Here: seekr2_b200_kick -> applyConstraints -> seekr2_b200_finish (decision + bounce on the device);
- * the crossing records are drained when the ring is polled (every step by default, to keep OpenMM's
- * Context time in step for Elber's setTime(0); `drainInterval` steps otherwise).  The first-step test
- * (:205-210) and the Elber force-group check (:415-436) keep their exceptions and messages. */
+ * Here, per execute():
+ *   System without constraints and virtual sites (posDelta untouched between the passes):
+ *       seekr2_b200_resync (tiny: boundary-group atoms -> slab) + seekr2_b200_step -- ONE pass over the atoms, the whole
+ *       step (kick, drift, CV, crossing test, bounce, log, clock) in one launch;
+ *   otherwise: seekr2_b200_kick -> applyConstraints -> seekr2_b200_finish (one launch: decision + Part2 + bounce).
+ * execute() never waits for the device: the crossing records stay in the device ring, the step kernels report "something
+ * was appended" through mapped host memory (seekr2_b200_poll, no CUDA call), and only then is a drain queued behind the
+ * current step and collected by a later execute() once it has landed.  Blocking points -- where the files must be
+ * complete and Context time exact -- are computeKineticEnergy() and the destructor.  Elber's device-side setTime(0)
+ * (:545) reaches cu.setTime() with the drain that reports it.  SEEKR2_B200_ASYNC_DRAIN=0 restores the reference's
+ * behaviour (a blocking drain inside every execute()); crossing states (saveStateFileName) always use it.
+ * The first-step test (:205-210) and the Elber force-group check (:415-436) keep their exceptions and messages. */
 #include "B200Seekr2Kernels.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
@@ -35,6 +43,11 @@ void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, i
     cu.setAsCurrent();
     cu.getIntegrationUtilities().initRandomNumberGenerator(seed);  /* :109 -- OpenMM's pool is used */
     boundarySet = recogniseBoundaries(system);
+    slotIndex = boundarySet.groupAtoms;                             /* identity order until OpenMM reorders */
+    /* one launch for the whole step needs posDelta untouched between the passes: no constraints, no virtual sites */
+    fused = system.getNumConstraints() == 0;
+    for (int i = 0; i < system.getNumParticles() && fused; i++) fused = !system.isVirtualSite(i);
+    if (const char* f = getenv("SEEKR2_B200_ADAPTER_FUSED")) if (f[0] == '0') fused = false;    /* A/B knob */
     cfg.abi_version = SEEKR2_B200_ABI_VERSION;
     cfg.precision = cu.getUseDoublePrecision() ? SEEKR2_B200_DOUBLE : cu.getUseMixedPrecision() ? SEEKR2_B200_MIXED : SEEKR2_B200_SINGLE;
     cfg.variant = SEEKR2_B200_VARIANT_CUDA;
@@ -48,9 +61,11 @@ void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, i
     cfg.group_weights = boundarySet.groupWeights.data();
     cfg.num_boundaries = (int) boundarySet.boundaries.size();
     cfg.boundaries = boundarySet.boundaries.data();
-    /* asynchronous drain: MMVT only (Elber mirrors the context time every step), and not while crossing states are
-       saved (their atom order is the one of the crossing step, and OpenMM may reorder atoms before a late collection) */
-    if (const char* a = getenv("SEEKR2_B200_ASYNC_DRAIN")) asyncDrain = a[0] == '1' && cfg.kind == SEEKR2_B200_KIND_MMVT && saveStateFileName.empty();
+    /* asynchronous drain unless crossing states are saved (their atom order is the one of the crossing step, and OpenMM
+       may reorder atoms before a late collection) */
+    asyncDrain = saveStateFileName.empty();
+    if (const char* a = getenv("SEEKR2_B200_ASYNC_DRAIN")) asyncDrain = asyncDrain && a[0] != '0';
+    kind = cfg.kind;
     /* the ring is drained in the step that crossed, so two slots are plenty */
     cfg.save_state_slots = saveStateFileName.empty() ? 0 : 2;
     check(seekr2_b200_create(&cfg, &handle));
@@ -79,16 +94,38 @@ void B200StepKernelBase::updateParams(double temperature, double friction, doubl
     }
 }
 
+/* cu.getAtomIndex()[i] = the particle held at buffer index i (CudaContext reorders atoms for its neighbour list,
+   cu.reorderAtoms() at :365, also from setPositions): the boundary groups name particles, the engine wants buffer
+   indices.  A handful of comparisons per step; a full remap only when the order really changed. */
+void B200StepKernelBase::followAtomOrder() {
+    const std::vector<int>& order = cu.getAtomIndex();
+    bool same = true;
+    for (size_t s = 0; s < slotIndex.size() && same; s++) same = order[slotIndex[s]] == boundarySet.groupAtoms[s];
+    if (same) return;
+    std::vector<int32_t> indexOf(order.size());
+    for (size_t i = 0; i < order.size(); i++) indexOf[order[i]] = (int32_t) i;
+    check(seekr2_b200_set_atom_order(handle, indexOf.data(), (void*) cu.getCurrentStream()));
+    for (size_t s = 0; s < slotIndex.size(); s++) slotIndex[s] = indexOf[boundarySet.groupAtoms[s]];
+}
+
 void B200StepKernelBase::stepTwoPass(double temperature, double friction, double stepSize, double tolerance) {
     CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
     updateParams(temperature, friction, stepSize);
+    followAtomOrder();
     seekr2_b200_buffers b = buffers();
     void* stream = (void*) cu.getCurrentStream();
     const int randomIndex = integration.prepareRandomNumbers(cu.getPaddedNumAtoms());       /* :214 */
+    if (fused) {
+        /* Part1 + Part2 + CV + crossing + bounce + log + clock in one launch (:214-365); the slab of boundary-group
+           atoms is re-read first because anything may have touched posq / velm since the last step */
+        check(seekr2_b200_resync(handle, &b, stream));
+        check(seekr2_b200_step(handle, &b, (uint32_t) randomIndex, stream));
+        return;
+    }
     check(seekr2_b200_kick(handle, &b, (uint32_t) randomIndex, stream));                    /* Part1 :215-223 */
     integration.applyConstraints(tolerance);                                                /* :227 */
     check(seekr2_b200_finish(handle, &b, stream));                                          /* Part2 + CV + crossing + bounce :231-358 */
-    integration.computeVirtualSites();                                                      /* :239 (groups with virtual sites are refused) */
+    integration.computeVirtualSites();                                                      /* :239 (boundary groups with virtual sites are refused at initialize) */
 }
 
 void B200StepKernelBase::allocateScratch(bool needOldVelm, bool needOldDelta) {
@@ -101,7 +138,15 @@ void B200StepKernelBase::allocateScratch(bool needOldVelm, bool needOldDelta) {
 void B200StepKernelBase::stepMiddle(double temperature, double friction, double stepSize, double tolerance) {
     CudaIntegrationUtilities& integration = cu.getIntegrationUtilities();
     updateParams(temperature, friction, stepSize);
+    followAtomOrder();
     seekr2_b200_buffers b = buffers();
+    if (fused) {                                                    /* no solver between the parts: oldDelta == delta */
+        void* stream = (void*) cu.getCurrentStream();
+        const int randomIndex = integration.prepareRandomNumbers(cu.getPaddedNumAtoms());   /* :762 */
+        check(seekr2_b200_resync(handle, &b, stream));
+        check(seekr2_b200_step(handle, &b, (uint32_t) randomIndex, stream));
+        return;
+    }
     b.d_old_velm = (void*) oldVelm.getDevicePointer();
     b.d_old_delta = (void*) oldDelta.getDevicePointer();
     void* stream = (void*) cu.getCurrentStream();
@@ -116,19 +161,30 @@ void B200StepKernelBase::stepMiddle(double temperature, double friction, double 
 
 void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::vector<int32_t>& labels, int numSrc) {
     drainFile = file; drainKind = kind; drainLabels = labels; drainNumSrc = numSrc;
+    collected = false;
     if (asyncDrain) {
-        /* collect the drain begun by an earlier step if it has landed (never waits), then queue one behind this step */
+        /* collect the drain begun by an earlier step if it has landed (never waits) ... */
         const int64_t n = drainPending ? collectPending(false) : -1;
         if (n < 0) records.clear();                                /* nothing new this time */
+        /* ... and queue one behind this step only if the device has reported something to fetch: records appended, or
+           an Elber clock reset.  A plain read of mapped host memory -- on all but crossing steps execute() issues
+           nothing besides the step itself. */
         if (!drainPending) {
-            check(seekr2_b200_drain_begin(handle, 4096, (void*) cu.getCurrentStream()));
-            drainPending = true;
+            int64_t pending = 0, resets = 0;
+            check(seekr2_b200_poll(handle, &pending, &resets));
+            if (pending > 0 || resets != seenResets) {
+                seenResets = resets;
+                check(seekr2_b200_drain_begin(handle, 4096, (void*) cu.getCurrentStream()));
+                drainPending = true;
+                pendingClockValid = true;
+            }
         }
         return;
     }
     records.resize(4096);
     int64_t n = 0;
     check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
+    collected = true; clockValid = true;
     writeRecords(n);
 }
 
@@ -143,6 +199,7 @@ int64_t B200StepKernelBase::collectPending(bool block) {
     int64_t n = 0, waiting = 0;
     check(seekr2_b200_drain_end(handle, records.data(), (int64_t) records.size(), &n, &waiting));
     drainPending = false;
+    collected = true; clockValid = pendingClockValid;
     writeRecords(n);
     return n;
 }
@@ -154,11 +211,26 @@ void B200StepKernelBase::flushDrain() {
         records.resize(4096);
         int64_t n = 0;
         check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
+        collected = true; clockValid = true;
         writeRecords(n);
         total += n;
         if (n < (int64_t) 4096) break;
     }
-    if (total > 0) writeStatistics();
+    int64_t resets = 0;
+    check(seekr2_b200_poll(handle, nullptr, &resets));
+    seenResets = resets;
+    if (total > 0 && kind == SEEKR2_B200_KIND_MMVT) writeStatistics();
+}
+
+/* Context time as the device holds it (Elber sets it back to 0 on the device, :545): the clock that came with the latest
+   drain, advanced by the steps issued since (the same repeated addition the device does, so the bits agree).  Returns
+   false when no usable clock has been collected. */
+bool B200StepKernelBase::deviceTime(long long stepsIssued, double stepSize, double& time) {
+    if (!collected || !clockValid) return false;
+    int64_t at = 0;
+    check(seekr2_b200_drain_clock(handle, 0, &time, &at));
+    for (long long k = at; k < stepsIssued; k++) time += stepSize;
+    return true;
 }
 
 /* CudaSeekr2Kernels.cpp:313-345: rewritten whenever crossings have been logged */
@@ -209,6 +281,7 @@ void B200MmvtStepKernel<K, I, MIDDLE>::initialize(const System& system, const I&
     const int32_t counter0 = integrator.getBounceCounter();        /* :151 */
     cfg.bounce_counter0 = &counter0;
     saveStateFileName = integrator.getSaveStateFileName();          /* :135-139 */
+    requireTypedMilestoneForces(system, {1});                       /* the hard-wired mask 2 (:206,:248) */
     create(system, cfg, integrator.getRandomNumberSeed());
     if (MIDDLE) allocateScratch(true, true);
     outputFileName = integrator.getOutputFileName();
@@ -226,6 +299,7 @@ void B200MmvtStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& in
         check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), stream));
     updateParams(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize());
     if (cu.getStepCount() <= 0) {                                  /* :205-210 */
+        followAtomOrder();
         seekr2_b200_buffers b = buffers();
         check(seekr2_b200_check_first_step(handle, &b, nullptr, stream));
     }
@@ -264,6 +338,11 @@ void B200ElberStepKernel<K, I, MIDDLE>::initialize(const System& system, const I
             for (int j = 0; j < system.getNumForces(); j++) found = found || system.getForce(j).getForceGroup() == group;
             if (!found) throw OpenMMException("System contains no force groups used to detect Elber boundary crossings. Check for mismatches between force group assignments and the groups added to the Elber integrator.");
         }
+    {
+        std::vector<int> used(src.begin(), src.end());
+        used.insert(used.end(), dest.begin(), dest.end());
+        requireTypedMilestoneForces(system, used);
+    }
     cfg.num_src = (int) src.size(); cfg.src_groups = src.data();
     cfg.num_dest = (int) dest.size(); cfg.dest_groups = dest.data();
     cfg.end_on_src_milestone = integrator.getEndOnSrcMilestone();  /* :414 */
@@ -283,21 +362,31 @@ template <class K, class I, bool MIDDLE>
 void B200ElberStepKernel<K, I, MIDDLE>::execute(ContextImpl& context, const I& integrator) {
     cu.setAsCurrent();
     void* stream = (void*) cu.getCurrentStream();
-    /* Elber's crossing test looks at the context time (:533,:558) and may reset it (:545): the engine
-       keeps that clock on the device; mirror OpenMM's copy into it before and out of it after */
-    check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), stream));
+    /* Elber's crossing test looks at the context time (:533,:558) and may reset it (:545): the engine keeps that clock on
+       the device.  OpenMM's copy follows it -- predicted as time + stepSize, corrected from the clock every drain carries
+       -- and is pushed to the device only when somebody else changed it (context.setTime, a new Context). */
+    if (first || cu.getTime() != expectedTime) {
+        check(seekr2_b200_set_time(handle, 0, cu.getTime(), cu.getStepCount(), stream));
+        pendingClockValid = false;                                  /* a drain still in flight carries the old clock */
+        first = false;
+    }
     if (MIDDLE) stepMiddle(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     else stepTwoPass(integrator.getTemperature(), integrator.getFriction(), integrator.getStepSize(), integrator.getConstraintTolerance());
     drainTo(outputFileName, SEEKR2_B200_KIND_ELBER, labels, numSrc);
-    seekr2_b200_anchor_state st;
-    check(seekr2_b200_get_state(handle, 0, &st, stream));
-    cu.setTime(st.time);                                           /* already advanced by stepSize (:592) */
+    double t = cu.getTime() + integrator.getStepSize();             /* :592, unless the device reset the clock */
+    deviceTime(cu.getStepCount() + 1, integrator.getStepSize(), t);
+    cu.setTime(t);
     cu.setStepCount(cu.getStepCount() + 1);
     cu.reorderAtoms();
+    expectedTime = t;
 }
 
 template <class K, class I, bool MIDDLE>
 double B200ElberStepKernel<K, I, MIDDLE>::computeKineticEnergy(ContextImpl&, const I& integrator) {
+    /* a natural synchronisation point: bring the file and Context time up to date */
+    flushDrain();
+    double t = 0;
+    if (deviceTime(cu.getStepCount(), integrator.getStepSize(), t)) { cu.setTime(t); expectedTime = t; }
     return cu.getIntegrationUtilities().computeKineticEnergy(0.5 * integrator.getStepSize());   /* :597-599, :1175-1177 */
 }
 

@@ -6,6 +6,7 @@
 #include "openmm/CustomCentroidBondForce.h"
 #include "openmm/OpenMMException.h"
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <regex>
 
@@ -38,6 +39,18 @@ Typed recognise(std::string e, int numGroups) {
 }
 }  // namespace
 
+/* The reference evaluates WHATEVER sits in a milestone's force group (calcForcesAndEnergy(false, true, mask),
+   CudaSeekr2Kernels.cpp:248,527,552); this implementation evaluates typed CustomCentroidBondForce terms only, so any
+   other Force in such a group must be refused rather than ignored. */
+void requireTypedMilestoneForces(const System& system, const std::vector<int>& forceGroups) {
+    for (int f = 0; f < system.getNumForces(); f++) {
+        const Force& force = system.getForce(f);
+        if (std::find(forceGroups.begin(), forceGroups.end(), force.getForceGroup()) == forceGroups.end()) continue;
+        if (dynamic_cast<const CustomCentroidBondForce*>(&force) == nullptr)
+            throw OpenMMException("B200 SEEKR2 plugin: force group " + std::to_string(force.getForceGroup()) + " is used to detect boundary crossings but holds a Force that is not a CustomCentroidBondForce");
+    }
+}
+
 B200BoundarySet recogniseBoundaries(const System& system) {
     B200BoundarySet out;
     /* identical groups (same particles, same weights) are lowered once: the reference's examples give every milestone
@@ -66,18 +79,32 @@ B200BoundarySet recogniseBoundaries(const System& system) {
         }
         std::map<std::string, int> index;
         for (int p = 0; p < force->getNumPerBondParameters(); p++) index[force->getPerBondParameterName(p)] = p;
-        auto value = [&](const std::vector<double>& params, const std::string& name, double fallback) {
-            auto it = index.find(name); return it == index.end() ? fallback : params[it->second]; };
+        /* every name in the expression must be a per-bond parameter (or a numeric literal): a global parameter, or a
+           name the Force does not define, would silently give a different surface than the reference evaluates */
+        auto value = [&](const std::vector<double>& params, const std::string& name) {
+            auto it = index.find(name);
+            if (it != index.end()) return params[it->second];
+            char* end = nullptr;
+            const double literal = std::strtod(name.c_str(), &end);
+            if (end != name.c_str() && *end == '\0') return literal;
+            throw OpenMMException("B200 SEEKR2 plugin: '" + name + "' in boundary expression '" + force->getEnergyFunction() + "' is not a per-bond parameter of the Force");
+        };
+        for (int g = 0; g < force->getNumGroups(); g++) {
+            std::vector<int> particles; std::vector<double> weights;
+            force->getGroupParameters(g, particles, weights);
+            for (int particle : particles)
+                if (system.isVirtualSite(particle)) throw OpenMMException("B200 SEEKR2 plugin: boundary groups containing virtual sites are not supported");
+        }
         for (int b = 0; b < force->getNumBonds(); b++) {
             std::vector<int> groups; std::vector<double> params;
             force->getBondParameters(b, groups, params);
             seekr2_b200_boundary bd{};
             bd.type = t.type; bd.style = t.style; bd.axis = t.axis; bd.force_group = force->getForceGroup();
             for (size_t g = 0; g < groups.size() && g < 6; g++) bd.groups[g] = remap[groups[g]];
-            bd.bitcode = value(params, "bitcode", 1.0);
-            bd.k = t.kSign * value(params, "k", 1.0);
-            bd.threshold = value(params, t.thr, 0.0);
-            if (t.type == SEEKR2_B200_CV_SPHERE_FIXED) { bd.center[0] = value(params, t.cx, 0); bd.center[1] = value(params, t.cy, 0); bd.center[2] = value(params, t.cz, 0); }
+            bd.bitcode = t.style == SEEKR2_B200_STYLE_STEP ? value(params, "bitcode") : 1.0;
+            bd.k = t.kSign * value(params, "k");
+            bd.threshold = value(params, t.thr);
+            if (t.type == SEEKR2_B200_CV_SPHERE_FIXED) { bd.center[0] = value(params, t.cx); bd.center[1] = value(params, t.cy); bd.center[2] = value(params, t.cz); }
             out.boundaries.push_back(bd);
         }
     }

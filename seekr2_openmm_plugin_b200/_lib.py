@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SEEKR2_B200_LIBRARY") or os.path.join(_HERE, "libseekr2_b200.so")   # override: A/B builds of the kernels
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "seekr2_b200.h")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_MILESTONES = 32
 MAX_BOUNDARIES = 32
 MAX_GROUPS = 16
@@ -92,7 +92,7 @@ class AnchorState(C.Structure):
         ("last_value_positive", C.c_int32),
         ("crossing_counter", C.c_int32), ("crossed_src", C.c_int32), ("end_simulation", C.c_int32),
         ("elber_sampled", C.c_int32), ("elber_values", C.c_float * MAX_ELBER),
-        ("num_snapshots", C.c_int32), ("reserved0", C.c_int32),
+        ("num_snapshots", C.c_int32), ("clock_resets", C.c_int32),
     ]
 
 
@@ -107,6 +107,9 @@ SYMBOLS = {
     "seekr2_b200_set_params": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "seekr2_b200_get_params": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "seekr2_b200_sync_groups": (C.c_int, [_P, C.POINTER(Buffers), _P]),
+    "seekr2_b200_resync": (C.c_int, [_P, C.POINTER(Buffers), _P]),
+    "seekr2_b200_set_atom_order": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
+    "seekr2_b200_poll": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "seekr2_b200_check_first_step": (C.c_int, [_P, C.POINTER(Buffers), C.POINTER(C.c_int32), _P]),
     "seekr2_b200_step": (C.c_int, [_P, C.POINTER(Buffers), C.c_uint32, _P]),
     "seekr2_b200_kick": (C.c_int, [_P, C.POINTER(Buffers), C.c_uint32, _P]),

@@ -45,6 +45,7 @@ struct EngineDev {
     unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
     unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
     long long* probe;            // optional timing probe (debug, seekr2_b200_debug_set_probe)
+    long long* hint;             // mapped pinned host memory [2][A]: ring head, clock resets -- written when they change (seekr2_b200_poll)
     int* head_start;             // [2] decide blocks that have issued their gathers (per launch parity)
     int first_wave_blocks;       // streaming blocks resident at kernel start (they wait for head_start)
     int head_start_target;       // A x warps per decide block that hold group slots
@@ -269,6 +270,7 @@ __device__ __forceinline__ void ring_append(const EngineDev& e, AnchorState& st,
     r.num_surfaces = nsurf; r.snapshot = snapshot; r.step = st.step_count; r.time = time;
     e.ring[(size_t) anchor * e.ring_capacity + (size_t) (st.ring_head % e.ring_capacity)] = r;
     st.ring_head++;
+    if (e.hint) e.hint[anchor] = st.ring_head;                      // crossing steps only: one posted write over PCIe
 }
 
 // The host block of CudaIntegrateMmvtLangevinStepKernel::execute (CudaSeekr2Kernels.cpp:250-347),
@@ -327,6 +329,8 @@ __device__ __forceinline__ int elber_bookkeeping(const EngineDev& e, AnchorState
             } else {
                 st.crossed_src = 1;
                 st.time = 0.0;                                      // context.setTime(0.0) :545
+                st.clock_resets++;
+                if (e.hint) e.hint[e.num_anchors + anchor] = st.clock_resets;
                 st.elber_values[i] = value;
             }
         }

@@ -80,6 +80,10 @@ struct seekr2_b200_engine {
     bool plain_next = true;         // the next fused launch is an ordinary one (no programmatic dependent launch): set whenever the step-index
                                     // shadow was (re)written by something other than the fused launch two steps back
     bool shadow_stale = false;      // two-pass steps advanced the clock but not the step-index shadow
+    int finish_parity = 0;          // half of decision[2][A] the next finish launch publishes in (the other half is cleared by it)
+    std::vector<int> group_atom_of_slot;   // slot -> atom index as given at create (seekr2_b200_set_atom_order maps it through the caller's order)
+    long long* h_hint = nullptr;    // mapped pinned [2][A]: ring heads and clock resets as the device last wrote them (seekr2_b200_poll)
+    long long drained_total = 0;    // records handed out by drain_end so far
     // device allocations
     int* d_slot_atom = nullptr;
     int* d_slot_group = nullptr;
@@ -111,6 +115,8 @@ struct seekr2_b200_engine {
     int capture_phase0 = 0;
     bool capture_plain0 = true;
     int capture_steps = 0;
+    int capture_finishes = 0;
+    int capture_finish_parity0 = 0;
     int graph_steps = 0;
 };
 
@@ -164,7 +170,7 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
         dim3 grid((unsigned) ((h->dev.num_slots + kThreads - 1) / kThreads), (unsigned) h->cfg.num_anchors, 1);
         gather_groups_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->phase & 1);
     }
-    decide_kernel<P, SEEKR2_B200_KIND_MMVT, 1><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
+    evaluate_kernel<P><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
     refresh_shadow_kernel<<<(h->cfg.num_anchors + 127) / 128, 128, 0, s>>>(h->dev, h->phase);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
@@ -246,12 +252,24 @@ template <int P> int launch_middle_drift(seekr2_b200_engine* h, const seekr2_b20
 }
 
 template <int P, int KIND> int launch_finish(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
-    // the pending position (posq + corr + posDelta) is the same expression in both schemes
-    decide_kernel<P, KIND, 0><<<h->cfg.num_anchors, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size);
+    // ONE launch: A decide blocks first (the pending position posq + corr + posDelta is the same expression in both schemes),
+    // then the streaming blocks, which wait for their anchor's decision word of this launch's parity
+    const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);
     if (h->cfg.scheme == SEEKR2_B200_SCHEME_MIDDLE)
-        middle_finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+        middle_finish_kernel<P, KIND><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, h->finish_parity, bpa);
     else
-        finish_kernel<P, KIND><<<atom_grid(h), kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h));
+        finish_kernel<P, KIND><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, h->finish_parity, bpa);
+    CUDA_TRY(cudaGetLastError());
+    h->finish_parity ^= 1;
+    if (h->capturing) h->capture_finishes++;
+    return SEEKR2_B200_OK;
+}
+
+template <int P> int launch_resync(seekr2_b200_engine* h, const seekr2_b200_buffers* b, cudaStream_t s) {
+    const int slots = h->dev.num_slots > 0 ? h->dev.num_slots : 1;
+    dim3 grid((unsigned) ((slots + kThreads - 1) / kThreads), (unsigned) h->cfg.num_anchors, 1);
+    resync_kernel<P><<<grid, kThreads, 0, s>>>(h->dev, typed_bufs<P>(b), h->phase);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }
@@ -294,6 +312,7 @@ int seekr2_b200_destroy(seekr2_b200_handle h) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_stage_hdr) cudaFreeHost(h->h_stage_hdr);
     if (h->h_stage_clock) cudaFreeHost(h->h_stage_clock);
+    if (h->h_hint) cudaFreeHost(h->h_hint);
     if (h->drain_event) cudaEventDestroy(h->drain_event);
     delete h;
     return SEEKR2_B200_OK;
@@ -485,8 +504,8 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     }
     CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));
-    CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * A));
-    CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * A));
+    CREATE_TRY(cudaMalloc(&h->d_decision, sizeof(int) * 2 * A));         // [2][A]: finish launches alternate halves
+    CREATE_TRY(cudaMemset(h->d_decision, 0, sizeof(int) * 2 * A));
     CREATE_TRY(cudaMalloc(&h->d_flags, sizeof(int) * (2 * A + 2)));      // [2][A] flags + [2] head-start counters
     CREATE_TRY(cudaMemset(h->d_flags, 0, sizeof(int) * (2 * A + 2)));
     CREATE_TRY(cudaMalloc(&h->d_step_shadow, sizeof(long long) * 4 * A));
@@ -513,6 +532,10 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     CREATE_TRY(cudaHostAlloc(&h->h_stage_clock, sizeof(long long) * 2 * A, cudaHostAllocMapped));
     memset(h->h_stage_clock, 0, sizeof(long long) * 2 * A);
     CREATE_TRY(cudaEventCreateWithFlags(&h->drain_event, cudaEventDisableTiming));
+    CREATE_TRY(cudaHostAlloc(&h->h_hint, sizeof(long long) * 2 * A, cudaHostAllocMapped));
+    memset(h->h_hint, 0, sizeof(long long) * 2 * A);
+    CREATE_TRY(cudaHostGetDevicePointer((void**) &d.hint, h->h_hint, 0));
+    h->group_atom_of_slot = slot_atom;
 
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
@@ -592,6 +615,49 @@ int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* buf
         h->plain_next = true;        // ... an ordinary launch: the next fused launch must not read the shadow before it has completed
     }
     return rc;
+}
+
+int seekr2_b200_resync(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream) {
+    if (int rc = check_bufs(h, bufs, false, false)) return rc;
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "resync cannot be captured");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t) stream;
+    int rc = DISPATCH_PRECISION(h, launch_resync<SINGLE>(h, bufs, s), launch_resync<MIXED>(h, bufs, s), launch_resync<DOUBLE>(h, bufs, s));
+    if (rc == SEEKR2_B200_OK) {
+        h->slab_valid = true;
+        h->shadow_stale = false;
+        h->plain_next = true;        // the shadow was written by an ordinary launch: the next fused launch must not read it early
+    }
+    return rc;
+}
+
+int seekr2_b200_set_atom_order(seekr2_b200_handle h, const int32_t* index_of_atom, void* stream) {
+    if (!h || !index_of_atom) return fail(SEEKR2_B200_ERR_INVALID, "null argument");
+    if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "set_atom_order cannot be captured");
+    DeviceGuard guard(h->device);
+    const size_t n = h->group_atom_of_slot.size();
+    if (n == 0) return SEEKR2_B200_OK;
+    std::vector<int> mapped(n);
+    for (size_t s = 0; s < n; s++) {
+        const int at = index_of_atom[h->group_atom_of_slot[s]];
+        if (at < 0 || at >= h->cfg.num_atoms) return fail(SEEKR2_B200_ERR_INVALID, "atom order maps atom %d to index %d outside [0,%d)", h->group_atom_of_slot[s], at, h->cfg.num_atoms);
+        mapped[s] = at;
+    }
+    // pageable source: the copy is staged before the call returns, and it is ordered behind the steps already queued on `stream`
+    CUDA_TRY(cudaMemcpyAsync(h->d_slot_atom, mapped.data(), sizeof(int) * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+    h->slab_valid = false;           // the slab was gathered (and is indexed) in the old order
+    return SEEKR2_B200_OK;
+}
+
+int seekr2_b200_poll(seekr2_b200_handle h, int64_t* records_pending, int64_t* clock_resets) {
+    if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
+    const int A = h->cfg.num_anchors;
+    const volatile long long* hint = h->h_hint;
+    long long appended = 0, resets = 0;
+    for (int a = 0; a < A; a++) { appended += hint[a]; resets += hint[A + a]; }
+    if (records_pending) *records_pending = appended - h->drained_total;
+    if (clock_resets) *clock_resets = resets;
+    return SEEKR2_B200_OK;
 }
 
 int seekr2_b200_check_first_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, int32_t* out_flags, void* stream) {
@@ -680,6 +746,8 @@ int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
     h->capturing = true;
     h->capture_phase0 = h->phase;
     h->capture_steps = 0;
+    h->capture_finishes = 0;
+    h->capture_finish_parity0 = h->finish_parity;
     h->capture_plain0 = h->plain_next;
     h->plain_next = true;            // the graph's first step has no kernel of this graph in front of it
     return SEEKR2_B200_OK;
@@ -695,6 +763,9 @@ int seekr2_b200_graph_end(seekr2_b200_handle h, void* stream) {
     h->phase = h->capture_phase0;        // the captured steps have not run yet
     h->plain_next = h->capture_plain0;
     h->graph_steps = h->capture_steps;
+    h->finish_parity = h->capture_finish_parity0;
+    if (h->capture_finishes & 1)
+        return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain an even number of two-pass steps (the decision half is baked into each finish launch); got %d", h->capture_finishes);
     if (h->graph_steps & 3)
         return fail(SEEKR2_B200_ERR_INVALID, "a step graph must contain a multiple of 4 fused steps (the launch phase is baked into each launch); got %d", h->graph_steps);
     CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
@@ -749,6 +820,7 @@ int seekr2_b200_drain_end(seekr2_b200_handle h, seekr2_b200_record* out, int64_t
         memcpy(out, h->h_stage, sizeof(Record) * (size_t) n);
     }
     *out_n = n;
+    h->drained_total += n;
     if (h->h_stage_hdr[1]) return fail(SEEKR2_B200_ERR_RING_OVERFLOW, "crossing ring overflowed: records were lost; drain more often or raise ring_capacity");
     return SEEKR2_B200_OK;
 }

@@ -202,7 +202,13 @@ class CustomCentroidBondForce(Force):
                 b.groups[gi] = remap[g] if remap is not None else group_base + g
             b.axis = t.axis
             b.force_group = self.getForceGroup()
-            b.bitcode = p.get("bitcode", 1.0)
+            # every name of the expression must be a per-bond parameter: no silent defaults (a global or misspelt
+            # parameter would give a different surface than the reference evaluates)
+            needed = (["bitcode"] if t.style == L.STYLE_STEP else []) + ["k", t.threshold_name] + list(t.center_names)
+            for name in needed:
+                if name not in p:
+                    raise L.Seekr2Error(L.ERR_INVALID, f"'{name}' in boundary expression '{self.expression}' is not a per-bond parameter of the Force")
+            b.bitcode = p["bitcode"] if t.style == L.STYLE_STEP else 1.0
             b.k = t.k_sign * p["k"]
             b.threshold = p[t.threshold_name]
             for c, name in enumerate(t.center_names):

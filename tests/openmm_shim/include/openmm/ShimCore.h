@@ -364,6 +364,8 @@ public:
     /* shim */
     ShimPlatformContext* shimContext;
     long long shimForceEvaluations, shimEnergyEvaluations;
+    long long shimForceNs, shimEnergyNs;        /* host time spent in force passes / energy-only passes */
+    double calcKineticEnergy() { return integrator.computeKineticEnergy(); }   /* OpenMM: ContextImpl::calcKineticEnergy() */
 private:
     friend class Context;
     Context& owner;

@@ -133,7 +133,7 @@ public:
     void setTime(double t) { time = t; }
     long long getStepCount() const { return stepCount; }
     void setStepCount(long long steps) { stepCount = steps; }
-    void reorderAtoms() {}
+    void reorderAtoms();
     /* ShimPlatformContext */
     void getPositions(std::vector<Vec3>& positions);
     void getForcePositions(std::vector<Vec3>& positions);
@@ -147,8 +147,12 @@ public:
     /* shim */
     std::vector<double> shimInverseMasses() const;
     const System& getSystem() const { return system; }
-    long long shimKernelLaunches;
+    long long shimKernelLaunches, shimReorders = 0;
+    int shimIndexOfAtom(int particle) const { return indexOfAtom[particle]; }
 private:
+    int at(int particle) const { return indexOfAtom[particle]; }
+    std::vector<int> indexOfAtom;            /* inverse of atomIndex */
+    int reorderEvery, reorderCalls;
     const System& system;
     CudaPlatform::PlatformData& platformData;
     int deviceIndex, numAtoms, paddedNumAtoms, multiprocessors, computeCapability;

@@ -16,13 +16,15 @@
  *   milestone <forceGroup> | src <forceGroup> | dest <forceGroup>
  *   particle <mass> <x> <y> <z> <vx> <vy> <vz>
  *   constraint <i> <j> <distance>
- *   harmonic <i> <j> <length> <k>
+ *   harmonic <i> <j> <length> <k> [forceGroup]
  *   tether <k>                                  F = -k (x - x0), x0 = the initial positions
  *   centroid <groupsPerBond> <forceGroup> <expression>       followed by
  *     param <name> | group <n> <i...> | wgroup <n> <i...> <w...> | bond <g...> : <p...> | end
  *   pool <path> <count>                         float32[count][4] normals, consumed 32*Np per pool refill
  *   steps <n> [<n> ...]                         several integrator.step() calls
  *   settime <t>                                 context.setTime(t) before the next steps directive
+ *   settle                                      ContextImpl::calcKineticEnergy() -- what getState(getEnergy=True) reaches: the
+ *                                               point at which an asynchronous platform must have its files and clock up to date
  *   dump <path>                                 final posq | posqCorrection | velm bytes + "time stepCount"
  */
 #include "ElberLangevinIntegrator.h"
@@ -37,7 +39,9 @@
 #include "openmm/cuda/CudaContext.h"
 #include "openmm/cuda/CudaPlatform.h"
 #include "openmm/internal/ContextImpl.h"
+#include <chrono>
 #include <cstdio>
+#include <cuda_runtime.h>
 #include <fstream>
 #include <iostream>
 #include <memory>
@@ -67,7 +71,7 @@ private:
     std::vector<Vec3> x0;
 };
 
-struct Action { enum Kind { Steps, SetTime } kind; int steps; double time; };
+struct Action { enum Kind { Steps, SetTime, Settle } kind; int steps; double time; };
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -109,9 +113,10 @@ int main(int argc, char* argv[]) {
             }
             else if (word == "constraint") { int i, j; double d; ls >> i >> j >> d; system.addConstraint(i, j, d); }
             else if (word == "harmonic") {
-                int i, j; double length, k; ls >> i >> j >> length >> k;
+                int i, j, group = 0; double length, k; ls >> i >> j >> length >> k;
                 HarmonicBondForce* f = new HarmonicBondForce();
                 f->addBond(i, j, length, k);
+                if (ls >> group) f->setForceGroup(group);
                 system.addForce(f);
             }
             else if (word == "tether") ls >> tetherK;
@@ -146,6 +151,7 @@ int main(int argc, char* argv[]) {
             else if (word == "pool") ls >> poolPath >> poolCount;
             else if (word == "steps") { int n; while (ls >> n) actions.push_back(Action{Action::Steps, n, 0}); }
             else if (word == "settime") { double t; ls >> t; actions.push_back(Action{Action::SetTime, 0, t}); }
+            else if (word == "settle") actions.push_back(Action{Action::Settle, 0, 0});
             else if (word == "dump") ls >> dumpPath;
             else throw OpenMMException("unknown directive " + word);
         }
@@ -199,10 +205,18 @@ int main(int argc, char* argv[]) {
             Context context(system, *integrator, platform, properties);
             context.setPositions(positions);
             context.setVelocities(velocities);
+            std::vector<double> stepSeconds;                      /* wall time of every steps directive, device drained */
             try {
                 for (const Action& a : actions) {
                     if (a.kind == Action::SetTime) context.setTime(a.time);
-                    else integrator->step(a.steps);
+                    else if (a.kind == Action::Settle) context.getImpl().calcKineticEnergy();
+                    else {
+                        cudaDeviceSynchronize();
+                        const auto t0 = std::chrono::steady_clock::now();
+                        integrator->step(a.steps);
+                        cudaDeviceSynchronize();
+                        stepSeconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+                    }
                 }
             } catch (const std::exception& e) {
                 std::cout << "step exception: " << e.what() << std::endl;
@@ -225,7 +239,11 @@ int main(int argc, char* argv[]) {
             }
             std::cout << "time " << cu.getTime() << " stepCount " << cu.getStepCount()
                       << " forceEvaluations " << impl.shimForceEvaluations << " energyEvaluations " << impl.shimEnergyEvaluations
-                      << " shimKernelLaunches " << cu.shimKernelLaunches << std::endl;
+                      << " shimKernelLaunches " << cu.shimKernelLaunches << " shimReorders " << cu.shimReorders
+                      << " forceNs " << impl.shimForceNs << " energyNs " << impl.shimEnergyNs << std::endl;
+            std::cout << "stepSeconds";
+            for (double t : stepSeconds) std::cout << " " << t;
+            std::cout << std::endl;
         }
         std::cout << (status == 0 ? "Done" : "Failed") << std::endl;
         return status;

@@ -108,11 +108,15 @@ CudaContext::CudaContext(const System& system, int deviceIndex, const std::strin
     if (useMixed) posqCorrection.initialize(*this, paddedNumAtoms, real4, "posqCorrection");
     velm.initialize(*this, paddedNumAtoms, mixed4, "velm");
     force.initialize(*this, 3 * (size_t) paddedNumAtoms, sizeof(long long), "force");
+    atomIndex.resize(numAtoms);
+    indexOfAtom.resize(numAtoms);
+    for (int i = 0; i < numAtoms; i++) atomIndex[i] = indexOfAtom[i] = i;
     /* velm.w = 1/mass, 0 for massless particles and padding */
     std::vector<Vec3> zero(numAtoms);
     setVelocities(zero);
-    atomIndex.resize(numAtoms);
-    for (int i = 0; i < numAtoms; i++) atomIndex[i] = i;
+    reorderCalls = 0;
+    reorderEvery = 0;
+    if (const char* r = std::getenv("OPENMM_SHIM_REORDER_EVERY")) reorderEvery = std::atoi(r);
     system.getDefaultPeriodicBoxVectors(box[0], box[1], box[2]);
     integration = new CudaIntegrationUtilities(*this, system);
 }
@@ -210,11 +214,11 @@ void CudaContext::getForcePositions(std::vector<Vec3>& positions) {
     if (useDouble) {
         std::vector<double> p(4 * (size_t) paddedNumAtoms);
         posq.download(p.data());
-        for (int i = 0; i < numAtoms; i++) positions[i] = Vec3(p[4 * i], p[4 * i + 1], p[4 * i + 2]);
+        for (int i = 0; i < numAtoms; i++) positions[i] = Vec3(p[4 * at(i)], p[4 * at(i) + 1], p[4 * at(i) + 2]);
     } else {
         std::vector<float> p(4 * (size_t) paddedNumAtoms);
         posq.download(p.data());
-        for (int i = 0; i < numAtoms; i++) positions[i] = Vec3(p[4 * i], p[4 * i + 1], p[4 * i + 2]);
+        for (int i = 0; i < numAtoms; i++) positions[i] = Vec3(p[4 * at(i)], p[4 * at(i) + 1], p[4 * at(i) + 2]);
     }
 }
 void CudaContext::getPositions(std::vector<Vec3>& positions) {
@@ -222,22 +226,22 @@ void CudaContext::getPositions(std::vector<Vec3>& positions) {
     if (useMixed) {
         std::vector<float> c(4 * (size_t) paddedNumAtoms);
         posqCorrection.download(c.data());
-        for (int i = 0; i < numAtoms; i++) positions[i] += Vec3(c[4 * i], c[4 * i + 1], c[4 * i + 2]);
+        for (int i = 0; i < numAtoms; i++) positions[i] += Vec3(c[4 * at(i)], c[4 * at(i) + 1], c[4 * at(i) + 2]);
     }
 }
 void CudaContext::setPositions(const std::vector<Vec3>& positions) {
     if (useDouble) {
         std::vector<double> p(4 * (size_t) paddedNumAtoms, 0.0);
         posq.download(p.data());
-        for (int i = 0; i < numAtoms; i++) for (int k = 0; k < 3; k++) p[4 * i + k] = positions[i][k];
+        for (int i = 0; i < numAtoms; i++) for (int k = 0; k < 3; k++) p[4 * at(i) + k] = positions[i][k];
         posq.upload(p.data());
     } else {
         std::vector<float> p(4 * (size_t) paddedNumAtoms, 0.0f), c(4 * (size_t) paddedNumAtoms, 0.0f);
         posq.download(p.data());
         for (int i = 0; i < numAtoms; i++)
             for (int k = 0; k < 3; k++) {
-                p[4 * i + k] = (float) positions[i][k];
-                c[4 * i + k] = (float) (positions[i][k] - (double) p[4 * i + k]);
+                p[4 * at(i) + k] = (float) positions[i][k];
+                c[4 * at(i) + k] = (float) (positions[i][k] - (double) p[4 * at(i) + k]);
             }
         posq.upload(p.data());
         if (useMixed) posqCorrection.upload(c.data());
@@ -248,29 +252,29 @@ void CudaContext::getVelocities(std::vector<Vec3>& velocities) {
     if (useDouble || useMixed) {
         std::vector<double> v(4 * (size_t) paddedNumAtoms);
         velm.download(v.data());
-        for (int i = 0; i < numAtoms; i++) velocities[i] = Vec3(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+        for (int i = 0; i < numAtoms; i++) velocities[i] = Vec3(v[4 * at(i)], v[4 * at(i) + 1], v[4 * at(i) + 2]);
     } else {
         std::vector<float> v(4 * (size_t) paddedNumAtoms);
         velm.download(v.data());
-        for (int i = 0; i < numAtoms; i++) velocities[i] = Vec3(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+        for (int i = 0; i < numAtoms; i++) velocities[i] = Vec3(v[4 * at(i)], v[4 * at(i) + 1], v[4 * at(i) + 2]);
     }
 }
 void CudaContext::setVelocities(const std::vector<Vec3>& velocities) {
     const std::vector<double> w = shimInverseMasses();
     if (useDouble || useMixed) {
         std::vector<double> v(4 * (size_t) paddedNumAtoms, 0.0);
-        for (int i = 0; i < numAtoms; i++) { for (int k = 0; k < 3; k++) v[4 * i + k] = velocities[i][k]; v[4 * i + 3] = w[i]; }
+        for (int i = 0; i < numAtoms; i++) { for (int k = 0; k < 3; k++) v[4 * at(i) + k] = velocities[i][k]; v[4 * at(i) + 3] = w[i]; }
         velm.upload(v.data());
     } else {
         std::vector<float> v(4 * (size_t) paddedNumAtoms, 0.0f);
-        for (int i = 0; i < numAtoms; i++) { for (int k = 0; k < 3; k++) v[4 * i + k] = (float) velocities[i][k]; v[4 * i + 3] = (float) w[i]; }
+        for (int i = 0; i < numAtoms; i++) { for (int k = 0; k < 3; k++) v[4 * at(i) + k] = (float) velocities[i][k]; v[4 * at(i) + 3] = (float) w[i]; }
         velm.upload(v.data());
     }
 }
 void CudaContext::setForces(const std::vector<Vec3>& forces) {
     std::vector<long long> f(3 * (size_t) paddedNumAtoms, 0);
     for (int i = 0; i < numAtoms; i++)
-        for (int k = 0; k < 3; k++) f[i + (size_t) k * paddedNumAtoms] = (long long) std::llrint(forces[i][k] * 4294967296.0);
+        for (int k = 0; k < 3; k++) f[at(i) + (size_t) k * paddedNumAtoms] = (long long) std::llrint(forces[i][k] * 4294967296.0);
     force.upload(f.data());
 }
 void CudaContext::getForces(std::vector<Vec3>& forces) {
@@ -278,8 +282,37 @@ void CudaContext::getForces(std::vector<Vec3>& forces) {
     force.download(f.data());
     forces.resize(numAtoms);
     for (int i = 0; i < numAtoms; i++)
-        forces[i] = Vec3(f[i] / 4294967296.0, f[i + (size_t) paddedNumAtoms] / 4294967296.0, f[i + 2 * (size_t) paddedNumAtoms] / 4294967296.0);
+        forces[i] = Vec3(f[at(i)] / 4294967296.0, f[at(i) + (size_t) paddedNumAtoms] / 4294967296.0, f[at(i) + 2 * (size_t) paddedNumAtoms] / 4294967296.0);
 }
+/* OpenMM's CudaContext::reorderAtoms() sorts atoms along a space-filling curve every few hundred steps when a cutoff is in
+   use; integrator kernels must therefore never assume particle i sits at buffer index i.  The stand-in has no neighbour
+   list, so it offers the same hazard on request: OPENMM_SHIM_REORDER_EVERY=n applies a fixed permutation (rotate by 7
+   within blocks of 16, then reverse) to posq / posqCorrection / velm and to atomIndex on every n-th call. */
+void CudaContext::reorderAtoms() {
+    if (reorderEvery <= 0 || ++reorderCalls % reorderEvery != 0 || numAtoms < 2) return;
+    std::vector<int> perm(numAtoms);                            /* new index -> old index */
+    for (int i = 0; i < numAtoms; i++) {
+        const int block = i / 16 * 16, width = std::min(16, numAtoms - block);
+        perm[numAtoms - 1 - i] = block + (i - block + 7) % width;
+    }
+    auto permute = [&](CudaArray& a) {
+        const size_t elem = a.getElementSize();
+        std::vector<char> in(a.getSize() * elem), out(a.getSize() * elem);
+        a.download(in.data());
+        out = in;
+        for (int i = 0; i < numAtoms; i++) std::memcpy(&out[i * elem], &in[perm[i] * elem], elem);
+        a.upload(out.data());
+    };
+    permute(posq);
+    if (useMixed) permute(posqCorrection);
+    permute(velm);
+    std::vector<int> newIndex(numAtoms);
+    for (int i = 0; i < numAtoms; i++) newIndex[i] = atomIndex[perm[i]];
+    atomIndex = newIndex;
+    for (int i = 0; i < numAtoms; i++) indexOfAtom[atomIndex[i]] = i;
+    shimReorders++;
+}
+
 void CudaContext::applyConstraints(double tol) {
     /* Context::applyConstraints: move the positions themselves onto the constraints */
     if (system.getNumConstraints() == 0) return;
@@ -395,16 +428,16 @@ void CudaIntegrationUtilities::shimRattle(const std::vector<Vec3>& x, std::vecto
 }
 
 namespace {
-void downloadDelta(CudaArray& posDelta, int n, std::vector<Vec3>& delta, std::vector<double>& raw64, std::vector<float>& raw32) {
+void downloadDelta(CudaContext& cu, CudaArray& posDelta, int n, std::vector<Vec3>& delta, std::vector<double>& raw64, std::vector<float>& raw32) {
     delta.resize(n);
     if (posDelta.getElementSize() == 32) {
         raw64.resize(4 * posDelta.getSize());
         posDelta.download(raw64.data());
-        for (int i = 0; i < n; i++) delta[i] = Vec3(raw64[4 * i], raw64[4 * i + 1], raw64[4 * i + 2]);
+        for (int i = 0; i < n; i++) { const int a = cu.shimIndexOfAtom(i); delta[i] = Vec3(raw64[4 * a], raw64[4 * a + 1], raw64[4 * a + 2]); }
     } else {
         raw32.resize(4 * posDelta.getSize());
         posDelta.download(raw32.data());
-        for (int i = 0; i < n; i++) delta[i] = Vec3(raw32[4 * i], raw32[4 * i + 1], raw32[4 * i + 2]);
+        for (int i = 0; i < n; i++) { const int a = cu.shimIndexOfAtom(i); delta[i] = Vec3(raw32[4 * a], raw32[4 * a + 1], raw32[4 * a + 2]); }
     }
 }
 }  // namespace
@@ -416,13 +449,13 @@ void CudaIntegrationUtilities::applyConstraints(double tol) {
     std::vector<Vec3> x, delta;
     std::vector<double> raw64; std::vector<float> raw32;
     context.getPositions(x);
-    downloadDelta(posDelta, n, delta, raw64, raw32);
+    downloadDelta(context, posDelta, n, delta, raw64, raw32);
     shimShake(x, delta, tol);
     if (posDelta.getElementSize() == 32) {
-        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) raw64[4 * i + k] = delta[i][k];
+        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) raw64[4 * context.shimIndexOfAtom(i) + k] = delta[i][k];
         posDelta.upload(raw64.data());
     } else {
-        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) raw32[4 * i + k] = (float) delta[i][k];
+        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) raw32[4 * context.shimIndexOfAtom(i) + k] = (float) delta[i][k];
         posDelta.upload(raw32.data());
     }
 }

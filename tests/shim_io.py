@@ -13,7 +13,8 @@ def _g(x):
 
 
 def write_scenario(path, syn, kind, precision, steps_list, pool=None, output="", savestate="", savestats="",
-                   counter=0, end_on_src=None, milestones=(), srcs=(), dests=(), dump="", settime_before=None):
+                   counter=0, end_on_src=None, milestones=(), srcs=(), dests=(), dump="", settime_before=None, settle=False,
+                   extra_lines=()):
     lines = [f"precision {precision}", f"integrator {kind} {_g(syn.temperature)} {_g(syn.friction)} {_g(syn.dt)}"]
     if output:
         lines.append(f"output {output}")
@@ -51,6 +52,9 @@ def write_scenario(path, syn, kind, precision, steps_list, pool=None, output="",
         if settime_before is not None and settime_before[0] == i:
             lines.append(f"settime {_g(settime_before[1])}")
         lines.append(f"steps {n}")
+    if settle:
+        lines.append("settle")        # ContextImpl::calcKineticEnergy(): an asynchronous platform brings files and clock up to date
+    lines += list(extra_lines)
     if dump:
         lines.append(f"dump {dump}")
     with open(path, "w") as fh:

@@ -57,12 +57,17 @@ def test_reference_platform_tests_pass_on_the_reference_platform_under_the_shim(
 from shim_io import PRECISIONS, read_dump, write_scenario  # noqa: E402
 
 
-def run_both(tmp_path, syn, kind, precision, steps_list, pool=None, want_rc=0, **kw):
+# how the adapter steps and drains (platforms/b200/src/B200Seekr2Kernels.cpp): by default one fused launch per step when the
+# System has no constraints, and an asynchronous drain; the knobs force the two-pass kernels / the blocking per-step drain
+ADAPTER_MODES = {"default": {}, "two_pass": {"SEEKR2_B200_ADAPTER_FUSED": "0"}, "blocking_drain": {"SEEKR2_B200_ASYNC_DRAIN": "0"}}
+
+
+def run_both(tmp_path, syn, kind, precision, steps_list, pool=None, want_rc=0, env=None, sides=("ref", "b200"), **kw):
     """Same scenario through ref_scenario (reference CUDA platform) and b200_scenario (this repository)."""
     out = {}
-    for side in ("ref", "b200"):
+    for side in sides:
         d = tmp_path / side
-        d.mkdir(exist_ok=True)
+        d.mkdir(parents=True, exist_ok=True)
         names = {k: str(d / k) for k in ("crossings.txt", "stats.txt", "state", "dump.bin")}
         extra = dict(kw)
         use_state = extra.pop("savestate", False)
@@ -70,7 +75,8 @@ def run_both(tmp_path, syn, kind, precision, steps_list, pool=None, want_rc=0, *
         scen = str(d / "scenario.txt")
         write_scenario(scen, syn, kind, precision, steps_list, pool, output=names["crossings.txt"], dump=names["dump.bin"],
                        savestate=names["state"] if use_state else "", savestats=names["stats.txt"] if use_stats else "", **extra)
-        proc = subprocess.run([_need(side + "_scenario"), scen], capture_output=True, text=True, timeout=600)
+        proc = subprocess.run([_need(side + "_scenario"), scen], capture_output=True, text=True, timeout=600,
+                              env={**os.environ, **(env or {})})
         assert proc.returncode == want_rc, f"{side}: rc {proc.returncode}\n{proc.stdout[-3000:]}\n{proc.stderr[-3000:]}"
         out[side] = (d, proc.stdout)
     return out
@@ -103,15 +109,18 @@ def assert_same_outputs(out, precision, n_atoms, states=False, stats=False, min_
 
 # ---- MMVT ----------------------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("mode", list(ADAPTER_MODES))
 @pytest.mark.parametrize("precision", ["single", "mixed", "double"])
 @pytest.mark.parametrize("kind", ["mmvt", "mmvt_middle"])
-def test_toy_mmvt_reference_platform_vs_b200_vs_oracle(cuda_device, tmp_path, kind, precision):
+def test_toy_mmvt_reference_platform_vs_b200_vs_oracle(cuda_device, tmp_path, kind, precision, mode):
     """C1 at 300 K with injected normals: crossings file, statistics file, saved states and final buffers of the
-    reference's CUDA platform == B200 adapter == CPU oracle."""
+    reference's CUDA platform == B200 adapter == CPU oracle.  (Crossing states are kept here, which makes every mode
+    drain inside the step; the asynchronous drain has its own test below.)"""
     syn = H.toy_system()
     steps = 3000
     pool = H.gaussian_pool(H.SEED_BASE + 41, steps * 32)
-    out = run_both(tmp_path, syn, kind, precision, [steps], pool, milestones=syn.milestone_groups, savestate=True, savestats=True)
+    out = run_both(tmp_path, syn, kind, precision, [steps], pool, milestones=syn.milestone_groups, savestate=True, savestats=True,
+                   env=ADAPTER_MODES[mode])
     lines, rb = assert_same_outputs(out, precision, 1, states=True, stats=True, min_lines=4)
     integ = H.make_mmvt_integrator(syn, "", middle=(kind == "mmvt_middle"))
     rc, o, ob = S.run_oracle(syn, integ, PRECISIONS[precision], steps, pool)
@@ -127,17 +136,66 @@ def test_toy_mmvt_reference_platform_vs_b200_vs_oracle(cuda_device, tmp_path, ki
     assert "energyEvaluations 0 " in out["b200"][1] and f"energyEvaluations {steps + 1} " in out["ref"][1]
 
 
+@pytest.mark.parametrize("mode", list(ADAPTER_MODES))
 @pytest.mark.parametrize("kind", ["mmvt", "mmvt_middle"])
-def test_adapter_asynchronous_drain_writes_the_same_files(cuda_device, tmp_path, kind, monkeypatch):
-    """SEEKR2_B200_ASYNC_DRAIN=1: the adapter's execute() never waits for the device (a drain is begun behind every step
-    and collected by a later step once it has landed; flushed at computeKineticEnergy / destruction).  Crossings file,
-    statistics file and final buffers still equal the reference CUDA platform's, which reads back and writes every step."""
-    monkeypatch.setenv("SEEKR2_B200_ASYNC_DRAIN", "1")          # read by the adapter only
+def test_adapter_asynchronous_drain_writes_the_same_files(cuda_device, tmp_path, kind, mode):
+    """No crossing states kept: the adapter's execute() never waits for the device (the step kernels report appended
+    records through mapped host memory; only then is a drain queued behind a step, and collected by a later step once it
+    has landed; flushed at computeKineticEnergy / destruction).  Crossings file, statistics file and final buffers still
+    equal the reference CUDA platform's, which reads back and writes every step."""
     syn = H.toy_system()
     pool = H.gaussian_pool(H.SEED_BASE + 43, 3000 * 32)
-    out = run_both(tmp_path, syn, kind, "mixed", [1000, 1500, 500], pool, milestones=syn.milestone_groups, savestats=True)
+    out = run_both(tmp_path, syn, kind, "mixed", [1000, 1500, 500], pool, milestones=syn.milestone_groups, savestats=True,
+                   env=ADAPTER_MODES[mode])
     lines, _ = assert_same_outputs(out, "mixed", 1, stats=True, min_lines=4)
     assert "energyEvaluations 0 " in out["b200"][1]
+
+
+@pytest.mark.parametrize("mode", ["default", "two_pass"])
+@pytest.mark.parametrize("kind", ["mmvt", "mmvt_middle", "elber"])
+def test_adapter_follows_atom_reordering(cuda_device, tmp_path, kind, mode):
+    """OpenMM's CUDA platform reorders atoms (cu.reorderAtoms(), CudaSeekr2Kernels.cpp:365); the stand-in does so on request
+    (a fixed permutation every 5th call).  The reference is immune -- its kernels treat all atoms alike and the boundary
+    Forces are OpenMM's -- while the adapter has to remap its boundary-group atoms (seekr2_b200_set_atom_order)."""
+    host, guest = list(range(0, 147)), list(range(147, 162))
+    env = {**ADAPTER_MODES[mode], "OPENMM_SHIM_REORDER_EVERY": "5"}
+    steps = 300
+    pool = H.gaussian_pool(H.SEED_BASE + 44, steps * 608)
+    if kind == "elber":
+        syn = H.pair_sphere_system(600, host, guest, 0.30, 0.50, H.SEED_BASE + 8, tether_k=300.0)
+        syn.system._forces = [f for f in syn.system._forces if not isinstance(f, s2.CustomCentroidBondForce)]
+        for group, radius in ((1, 0.40), (2, 0.397), (3, 0.403)):
+            f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+            g1, g2 = f.addGroup(host), f.addGroup(guest)
+            f.setForceGroup(group)
+            for name in ("bitcode", "k", "radius"):
+                f.addPerBondParameter(name)
+            f.addBond([g1, g2], [1.0, 1.0, radius])
+            syn.system.addForce(f)
+        H.place_pair_distance(syn, host, guest, 0.3995)
+        out = run_both(tmp_path, syn, kind, "mixed", [steps], pool, srcs=[1], dests=[2, 3], end_on_src=False, env=env, settle=True)
+        assert_same_outputs(out, "mixed", 600, min_lines=2)
+    else:
+        syn = H.pair_sphere_system(600, host, guest, 0.395, 0.405, H.SEED_BASE + 8, tether_k=300.0)
+        H.place_pair_distance(syn, host, guest, 0.40)
+        out = run_both(tmp_path, syn, kind, "mixed", [steps], pool, milestones=syn.milestone_groups, savestats=True, env=env)
+        assert_same_outputs(out, "mixed", 600, stats=True, min_lines=3)
+    assert f"shimReorders {steps // 5} " in out["b200"][1] and f"shimReorders {steps // 5} " in out["ref"][1]
+
+
+def test_adapter_refuses_what_it_cannot_type(cuda_device, tmp_path):
+    """The reference evaluates whatever sits in a milestone's force group; the adapter evaluates typed terms only and must
+    say so instead of silently using defaults: a name that is not a per-bond parameter, a non-centroid Force in the
+    MMVT force group."""
+    syn = S.ballistic_toy()
+    f = next(f for f in syn.system._forces if isinstance(f, s2.CustomCentroidBondForce))
+    f.param_names[f.param_names.index("radius")] = "rad"            # the expression still says radius
+    out = run_both(tmp_path / "a", syn, "mmvt", "mixed", [3], None, want_rc=1, milestones=[1, 2], sides=("b200",))
+    assert "is not a per-bond parameter" in out["b200"][1]
+    syn = S.ballistic_toy()
+    out = run_both(tmp_path / "b", syn, "mmvt", "mixed", [3], None, want_rc=1, milestones=[1, 2], sides=("b200",),
+                   extra_lines=["harmonic 0 0 0.1 1.0 1"])
+    assert "not a CustomCentroidBondForce" in out["b200"][1]
 
 
 def test_corner_bounce_rawstyle_restart_counter(cuda_device, tmp_path):
@@ -238,7 +296,10 @@ def test_elber_end_reset_and_asterisk(cuda_device, tmp_path, kind, end_on_src, s
     assert filecmp.cmp(opath, out["ref"][0] / "crossings.txt", shallow=False)
 
 
-def test_elber_thermal_host_guest(cuda_device, tmp_path):
+@pytest.mark.parametrize("mode", list(ADAPTER_MODES))
+def test_elber_thermal_host_guest(cuda_device, tmp_path, mode):
+    """No crossing states kept: asynchronous drain; Context time follows the device clock (which Elber resets, :545) through
+    the clock every drain carries -- exact again at the latest at calcKineticEnergy() (`settle`)."""
     host, guest = list(range(0, 11)), list(range(11, 20))
     syn = H.pair_sphere_system(300, host, guest, 0.30, 0.50, H.SEED_BASE + 5, tether_k=0.0)
     syn.system._forces = [f for f in syn.system._forces if not isinstance(f, s2.CustomCentroidBondForce)]
@@ -253,8 +314,19 @@ def test_elber_thermal_host_guest(cuda_device, tmp_path):
     H.place_pair_distance(syn, host, guest, 0.395)
     steps = 1500
     pool = H.gaussian_pool(H.SEED_BASE + 55, steps * 320)
-    out = run_both(tmp_path, syn, "elber", "mixed", [steps], pool, srcs=[1], dests=[2, 3], end_on_src=False)
+    out = run_both(tmp_path, syn, "elber", "mixed", [steps // 3, steps - steps // 3], pool, srcs=[1], dests=[2, 3], end_on_src=False,
+                   env=ADAPTER_MODES[mode], settle=True)
     assert_same_outputs(out, "mixed", 300, min_lines=3)
+
+
+@pytest.mark.parametrize("kind", ["elber", "elber_middle"])
+def test_elber_reset_reaches_context_time_without_crossing_states(cuda_device, tmp_path, kind):
+    """Source crossing resets the clock on the device; no state files, so the drain is asynchronous.  After `settle` the
+    Context time equals the reference's; a context.setTime() between two step() calls is followed."""
+    syn, integ = S.elber_ballistic(False, speed=0.5, middle=(kind == "elber_middle"))
+    out = run_both(tmp_path, syn, kind, "mixed", [40, 80], None, srcs=[1], dests=[2, 3], end_on_src=False, counter=5,
+                   settime_before=(1, 0.25), settle=True)
+    lines, rb = assert_same_outputs(out, "mixed", 1, min_lines=3)
 
 
 def test_elber_missing_force_group_message(cuda_device, tmp_path):

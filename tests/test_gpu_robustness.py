@@ -181,3 +181,78 @@ def test_drain_begin_end_contract(cuda_device):
     left = waiting.value
     assert L.lib.seekr2_b200_drain(h, buf, 4096, C.byref(n), stream) == L.OK and n.value == left
     assert integ.getAnchorState(0).ring_head == first + 5 + left
+
+
+def test_poll_reports_appended_records_without_a_cuda_call(cuda_device):
+    """seekr2_b200_poll reads mapped host memory only: the step kernels mirror the ring head there on crossing steps."""
+    syn = S.ballistic_toy(speed=5.0, dt=0.01)          # bounces every ~4 steps
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.drainInterval = 10 ** 9                       # step() below drains once, at its end
+    ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
+    ctx.setPositions(syn.positions)
+    ctx.setVelocities(syn.velocities)
+    pending, resets = C.c_int64(-1), C.c_int64(-1)
+    L.check(L.lib.seekr2_b200_poll(integ._handle, C.byref(pending), C.byref(resets)))
+    assert (pending.value, resets.value) == (0, 0)
+    integ._update_params(); ctx.prepareForces(); integ._first_step_check(); integ._before_first_step()
+    integ._issue(200)                                   # queued, nothing drained
+    import torch
+    torch.cuda.synchronize()
+    L.check(L.lib.seekr2_b200_poll(integ._handle, C.byref(pending), C.byref(resets)))
+    st = integ.getAnchorState(0)
+    assert pending.value == st.ring_head > 20
+    got = integ.drain()
+    assert len(got) == st.ring_head
+    L.check(L.lib.seekr2_b200_poll(integ._handle, C.byref(pending), C.byref(resets)))
+    assert pending.value == 0
+
+
+@pytest.mark.parametrize("precision", [L.SINGLE, L.MIXED, L.DOUBLE])
+def test_resync_every_step_and_permuted_atom_order(cuda_device, precision):
+    """What the OpenMM adapter does: seekr2_b200_resync in front of every fused step (the slab is re-read from the caller's
+    buffers), and seekr2_b200_set_atom_order when the caller's buffers hold the atoms in another order.  The same system
+    with its atoms stored in reversed order must evolve identically (in-kernel normals are keyed by buffer index, so an
+    injected pool, permuted alike, is used)."""
+    host, guest = list(range(0, 11)), list(range(11, 20))
+    n = 300
+    syn = H.pair_sphere_system(n, host, guest, 0.185, 0.195, H.SEED_BASE + 21, tether_k=0.0)
+    H.place_pair_distance(syn, host, guest, 0.19)
+    steps = 300
+    npad = (n + 31) // 32 * 32
+    pool = H.gaussian_pool(77, steps * npad)
+    integ = H.make_mmvt_integrator(syn, "")
+    rc, o, ob = S.run_oracle(syn, integ, precision, steps, pool)
+    assert rc == 0 and o.state().bounce_counter > 0
+
+    def run(order):
+        integ = H.make_mmvt_integrator(syn, "")
+        names = {L.SINGLE: "single", L.MIXED: "mixed", L.DOUBLE: "double"}
+        hb = H.make_host_buffers(precision, syn.positions, syn.velocities, syn.masses)
+        perm = np.arange(npad)
+        perm[:n] = order                                # buffer index i holds atom order[i]
+        hb.posq = hb.posq[perm].copy(); hb.velm = hb.velm[perm].copy()
+        if hb.corr is not None:
+            hb.corr = hb.corr[perm].copy()
+        ppool = pool.reshape(steps, npad, 4)[:, perm].reshape(-1, 4).copy()
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": names[precision]})
+        H.upload(ctx, [hb])
+        ctx.setRandomPool(ppool)
+        index_of = np.empty(n, dtype=np.int32)
+        index_of[order] = np.arange(n, dtype=np.int32)
+        L.check(L.lib.seekr2_b200_set_atom_order(integ._handle, index_of.ctypes.data_as(C.POINTER(C.c_int32)), ctx.stream_ptr))
+        integ._update_params(); ctx.prepareForces()
+        for s in range(steps):
+            bufs = ctx.buffers()
+            L.check(L.lib.seekr2_b200_resync(integ._handle, C.byref(bufs), ctx.stream_ptr))
+            L.check(L.lib.seekr2_b200_step(integ._handle, C.byref(bufs), s * npad, ctx.stream_ptr))
+        got = H.download(ctx)
+        inv = np.arange(npad); inv[perm] = np.arange(npad)
+        got.posq = got.posq[inv]; got.velm = got.velm[inv]
+        if got.corr is not None:
+            got.corr = got.corr[inv]
+        return got, integ.drain(), integ.getAnchorState(0)
+
+    for order in (np.arange(n), np.arange(n)[::-1].copy()):
+        got, recs, st = run(order)
+        H.assert_state_equal(ob, got, n, "resync + fused step vs oracle")
+        assert st.bounce_counter == o.state().bounce_counter and len(recs) == len(o.records())
