@@ -37,6 +37,8 @@ N_ATOMS = 23036         # tryp_ben.inpcrd:2
 LIG = [3221, 3222, 3223, 3224, 3225, 3226, 3227, 3228, 3229]                      # demo3:18
 REC = [2478, 2489, 2499, 2535, 2718, 2745, 2769, 2787, 2794, 2867, 2926]          # demo3:20
 STEPS_PER_GRAPH = 32
+LATENCY_STEPS = 4096        # the latency-regime legs (one anchor per GPU, host-guest, launch floor) always time this many
+                            # steps as whole 32-step graphs, whatever --steps says: a 20-step sample of a 2 us kernel is noise
 BYTES_PER_ATOM_STEP = 152   # mixed precision, in-kernel RNG: R velm 32 + force 24 + posq 16 + corr 16, W 64 (168 with a Gaussian pool)
 
 
@@ -63,6 +65,19 @@ def build_workload(num_anchors: int, n_atoms: int, seed: int):
     syn.positions = base
     forces = H.gaussian_pool(seed + 99, n_atoms)[:, :3].astype(np.float64)     # static, sigma = 1 kJ/mol/nm
     return syn, positions, forces, shells
+
+
+def ncu_traffic(anchors: int, atoms: int):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture), read from the committed summary of that capture -- a number measured under ncu once per code change, NOT in this
+    run; keyed by the workload it was captured on."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        table = json.load(open(path))
+        e = table[f"{anchors}x{atoms}"]
+        return float(e["dram_bytes_per_launch"]), f"profiles/{e['source']} (ncu --set full of this workload, captured {e['captured']}; not measured in this run)"
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -103,11 +118,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(num_anchors_per_thread: int, steps: int, warmup: int, n_atoms: int, seed: int) -> dict:
-    """The reference's CPU path (oracle port of the Reference platform, double precision,
-    VARIANT_REFERENCE incl. its three per-step copies) on all host cores, one anchor per thread."""
+def cpu_reference(n_atoms: int, seed: int, min_seconds: float = 2.0, repeats: int = 3) -> dict:
+    """The reference's CPU path -- the oracle port of the Reference platform (ReferenceSeekr2Kernels.cpp:195-339: double
+    precision, VARIANT_REFERENCE incl. its three per-step array copies) -- timed as SURVEY.md 8d asks: `repeats` runs of at
+    least `min_seconds` each, the median reported, once on ONE thread (the Reference platform is single-threaded) and once
+    with one anchor per host core (the all-core figure the GPU arm is compared with)."""
     import helpers as H                                         # tests/helpers.py: the ONLY place bench.py loads oracle/
-    from helpers import L, s2
+    from helpers import L
     cores = len(os.sched_getaffinity(0))
     syn, positions, forces, _ = build_workload(cores, n_atoms, seed)
     integ = H.make_mmvt_integrator(syn, "", "reference")
@@ -118,26 +135,136 @@ def cpu_reference(num_anchors_per_thread: int, steps: int, warmup: int, n_atoms:
         hb = H.make_host_buffers(L.DOUBLE, positions[a], syn.velocities, syn.masses, forces)
         pool = H.gaussian_pool(seed + a, chunk * hb.posq.shape[0])     # reused cyclically every `chunk` steps
         runs.append((o, hb, pool))
-    steps = max(chunk, steps // chunk * chunk)
 
     def work(idx, n):
         o, hb, pool = runs[idx]
         for _ in range(n // chunk):
             o.run(chunk, hb.posq, hb.corr, hb.velm, hb.force, pool, 0, None, 0.0)
 
-    def parallel(n):
-        ts = [threading.Thread(target=work, args=(i, n)) for i in range(cores)]
+    def parallel(threads, n):
+        ts = [threading.Thread(target=work, args=(i, n)) for i in range(threads)]
+        t0 = time.perf_counter()
         [t.start() for t in ts]
         [t.join() for t in ts]
+        return time.perf_counter() - t0
 
-    parallel(chunk * max(1, warmup // chunk))
-    t0 = time.perf_counter()
-    parallel(steps)
-    dt = time.perf_counter() - t0
-    value = ns_per_day(steps / dt) * cores
-    return {"value": value, "unit": "anchor-ns/day", "cores": cores, "kind": "port",
-            "sample": f"{cores} anchors x {n_atoms} atoms x {steps} steps, one anchor per thread, double precision, oracle restatement of ReferenceSeekr2Kernels.cpp:195-339",
-            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+    def measure(threads):
+        parallel(threads, chunk)                                # warm-up: page in, caches
+        n = chunk * 8
+        dt = parallel(threads, n)
+        n = max(chunk, int(n * min_seconds * 1.15 / dt) // chunk * chunk)     # steps per repeat for >= min_seconds
+        times = []
+        while len(times) < repeats:
+            dt = parallel(threads, n)
+            if dt < min_seconds:                                # the calibration run was slower than steady state: lengthen
+                n = int(n * min_seconds * 1.15 / dt) // chunk * chunk
+                times = []
+                continue
+            times.append(dt)
+        times.sort()
+        med = times[len(times) // 2]
+        return {"value": ns_per_day(n / med) * threads, "steps_per_repeat": n, "seconds": times, "ms_per_step": med / n * 1e3}
+
+    single = measure(1)
+    allc = measure(cores)
+    return {"value": allc["value"], "unit": "anchor-ns/day", "cores": cores, "kind": "port",
+            "sample": f"{cores} anchors x {n_atoms} atoms x {allc['steps_per_repeat']} steps, one anchor per thread, double precision, "
+                      f"median of {repeats} repeats of >= {min_seconds} s; oracle restatement of ReferenceSeekr2Kernels.cpp:195-339",
+            "seconds": allc["seconds"], "ms_per_step": allc["ms_per_step"], "steps": allc["steps_per_repeat"], "repeats": repeats,
+            "single_thread": {"value": single["value"], "unit": "anchor-ns/day", "cores": 1, "steps": single["steps_per_repeat"],
+                              "seconds": single["seconds"], "ms_per_step": single["ms_per_step"],
+                              "note": "the Reference platform itself is single-threaded (ReferenceSeekr2Kernels.cpp:195-339)"}}
+
+
+def adapter_vs_reference(seed: int) -> dict:
+    """Times `integrator.step(n)` of the reference's OWN integrator classes (compiled unmodified) on the "CUDA" platform of the
+    OpenMM stand-in (tests/openmm_shim -- NOT OpenMM, which is absent here), once with the reference's own CUDA-platform kernels
+    behind the kernel factory (`ref_scenario`: CudaSeekr2Kernels.cpp:175-366,465-595 + langevin.cu through NVRTC, unmodified)
+    and once with platforms/b200 (`b200_scenario`).  Both processes get the same scenario file; the force buffer is evaluated
+    once and then frozen and the Gaussian pool is filled once (OPENMM_SHIM_FREEZE_FORCES / OPENMM_SHIM_REUSE_POOL), so that the
+    wall time of step(n) is the integrator kernels' and not the stand-in's host-side force pass.  The reference's per-step
+    energy pass of the boundary force group (calcForcesAndEnergy(false, true, mask), :248 / :527,:552) is part of its execute();
+    under the stand-in it is a position download + a host evaluation, under a real OpenMM it would be a few small kernels + an
+    8-byte read-back -- so the time spent in it is reported separately and the reference is also quoted WITHOUT it (a lower
+    bound no real OpenMM can reach: the read-back alone synchronises every step).  The crossing files and the final
+    posq / posqCorrection / velm of the two runs must be identical."""
+    import filecmp
+    import tempfile
+    import helpers as H                                         # tests/: scenario writer shared with the parity tests
+    import shim_io
+    from helpers import s2
+    shim = os.path.join(ROOT, "oracle", "_ref", "shim")
+    if not all(os.path.exists(os.path.join(shim, b)) for b in ("ref_scenario", "b200_scenario")):
+        return {"unavailable": "oracle/_ref/shim binaries missing (oracle/build_shim.sh needs /root/reference)"}
+    warm, timed = 256, 4096
+    env = {**os.environ, "OPENMM_SHIM_FREEZE_FORCES": "1", "OPENMM_SHIM_REUSE_POOL": "1"}
+    out = {"steps_timed": timed, "warmup_steps": warm, "precision": "mixed",
+           "stand_in": "tests/openmm_shim (NOT OpenMM): forces frozen after the first evaluation, Gaussian pool filled once"}
+
+    def system(size, kind):
+        if size == "c2":
+            host, guest, n = list(range(0, 147)), list(range(147, 162)), 2520
+            rin, rout, dt = 0.37, 0.43, 0.002
+        else:
+            host, guest, n = REC, LIG, N_ATOMS
+            rin, rout, dt = 1.17, 1.23, DT_PS
+        syn = H.pair_sphere_system(n, host, guest, rin, rout, seed + 31, dt=dt, tether_k=0.0)
+        if kind == "elber":                                     # reflect / transmit pair around a source milestone (C3)
+            syn.system._forces = [f for f in syn.system._forces if not isinstance(f, s2.CustomCentroidBondForce)]
+            for group, radius in ((1, 0.5 * (rin + rout)), (2, rin), (3, rout)):
+                f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
+                g1, g2 = f.addGroup(host), f.addGroup(guest)
+                f.setForceGroup(group)
+                for name in ("bitcode", "k", "radius"):
+                    f.addPerBondParameter(name)
+                f.addBond([g1, g2], [1.0, 1.0, radius])
+                syn.system.addForce(f)
+        H.place_pair_distance(syn, host, guest, 0.5 * (rin + rout) + (0.004 if kind == "elber" else 0.0))
+        return syn, n
+
+    with tempfile.TemporaryDirectory() as tmp:
+        for size in ("c2", "c4"):
+            out[size] = {}
+            for kind in ("mmvt", "elber"):
+                syn, n = system(size, kind)
+                res = {}
+                for side in ("ref", "b200"):
+                    d = os.path.join(tmp, f"{size}_{kind}_{side}")
+                    os.makedirs(d)
+                    kw = dict(milestones=syn.milestone_groups) if kind == "mmvt" else dict(srcs=[1], dests=[2, 3], end_on_src=False)
+                    shim_io.write_scenario(os.path.join(d, "scenario.txt"), syn, kind, "mixed", [warm, timed], None,
+                                           output=os.path.join(d, "crossings.txt"), dump=os.path.join(d, "dump.bin"), settle=True, **kw)
+                    proc = subprocess.run([os.path.join(shim, side + "_scenario"), os.path.join(d, "scenario.txt")],
+                                          capture_output=True, text=True, env=env, timeout=600)
+                    if proc.returncode != 0:
+                        res[side] = {"error": (proc.stdout + proc.stderr)[-400:]}
+                        continue
+                    words = proc.stdout.split()
+                    secs = [float(x) for x in proc.stdout.split("stepSeconds")[1].split("\n")[0].split()]
+                    energy_ns = int(words[words.index("energyNs") + 1])
+                    energy_evals = int(words[words.index("energyEvaluations") + 1])
+                    us = secs[1] / timed * 1e6
+                    per_eval_us = energy_ns / max(1, energy_evals) * 1e-3
+                    res[side] = {"us_per_step": us, "energy_passes": energy_evals, "us_per_energy_pass": per_eval_us, "dir": d}
+                entry = {"atoms": n}
+                if "error" in res.get("ref", {}) or "error" in res.get("b200", {}):
+                    entry["error"] = {k: v.get("error") for k, v in res.items()}
+                else:
+                    r, b = res["ref"], res["b200"]
+                    passes_per_step = r["energy_passes"] / (warm + timed)
+                    entry.update({
+                        "reference_us_per_step": r["us_per_step"],
+                        "reference_energy_pass_us_per_step": r["us_per_energy_pass"] * passes_per_step,
+                        "reference_us_per_step_without_energy_pass": r["us_per_step"] - r["us_per_energy_pass"] * passes_per_step,
+                        "adapter_us_per_step": b["us_per_step"], "adapter_energy_passes": b["energy_passes"],
+                        "adapter_over_reference": b["us_per_step"] / r["us_per_step"],
+                        "adapter_over_reference_without_energy_pass": b["us_per_step"] / (r["us_per_step"] - r["us_per_energy_pass"] * passes_per_step),
+                        "crossings_files_identical": filecmp.cmp(os.path.join(r["dir"], "crossings.txt"), os.path.join(b["dir"], "crossings.txt"), shallow=False),
+                        "final_buffers_identical": filecmp.cmp(os.path.join(r["dir"], "dump.bin"), os.path.join(b["dir"], "dump.bin"), shallow=False),
+                        "crossing_lines": sum(1 for _ in open(os.path.join(r["dir"], "crossings.txt"))),
+                    })
+                out[size][kind] = entry
+    return out
 
 
 def main() -> None:
@@ -152,7 +279,10 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-box", action="store_true")
+    ap.add_argument("--no-adapter", action="store_true")
     args = ap.parse_args()
+    if args.impl == "reference":
+        os.environ["SEEKR2_B200_STRUCTS_ONLY"] = "1"      # struct definitions only: the CPU arm never loads libseekr2_b200.so
 
     # stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner,
     # torch warnings) is sent to stderr, and the line is written to the saved descriptor at the end
@@ -168,26 +298,32 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     seed = 0x5EEC2000 + 4
+    # the headline honours --steps: it is replayed as CUDA graphs of G steps, G = the largest multiple of 4 that is <= 32 and
+    # <= --steps (the launch phase is baked into a captured launch), plus at most 3 eager launches; the warm-up is rounded up
+    # to whole graphs so that the graph is instantiated and warm before the timed region
+    G = min(STEPS_PER_GRAPH, args.steps // 4 * 4)
     W = max(3, args.warmup)
-    W = (W + STEPS_PER_GRAPH - 1) // STEPS_PER_GRAPH * STEPS_PER_GRAPH   # whole graphs, so the step graph is warm
+    if G >= 4:
+        W = (W + G - 1) // G * G
     config = {"workload": f"C4 trypsin-benzamidine-like MMVT: {args.atoms} atoms, {args.anchors} anchors (0.2 nm shells) batched per GPU, "
                           "11+9-atom centroid-pair spherical milestones, dt 4 fs, 300 K, 1/ps, CudaPrecision=mixed",
               "atoms": args.atoms, "anchors_per_gpu": args.anchors, "dt_fs": DT_PS * 1e3,
               "l2": "inputs larger than L2: state 260 MB + force 71 MB per step vs 126 MB L2; no flush needed",
               "force": "static synthetic force buffer (the step's input)", "rng": "in-kernel Philox4x32-10 + Box-Muller (no Gaussian pool)",
-              "steps_per_graph": STEPS_PER_GRAPH}
+              "steps_per_graph": G, "eager_steps": args.steps - (args.steps // G * G if G >= 4 else 0), "warmup_requested": args.warmup,
+              "warmup_rounded_to": W, "latency_legs_steps": LATENCY_STEPS}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_steps = args.cpu_steps or max(16, min(args.steps * 16, 32000))
-        res = cpu_reference(1, cpu_steps, 16, args.atoms, seed)
-        cpu_steps = int(round(res['ms_per_step'] and res['seconds'] / (res['ms_per_step'] * 1e-3)))
+        res = cpu_reference(args.atoms, seed)
         line = {"impl": "reference", "metric": "mmvt_aggregate_anchor_ns_per_day", "value": res["value"], "unit": "anchor-ns/day",
-                "n_gpus": args.gpus, "steps": cpu_steps, "warmup": 16, "ms_per_step": res["ms_per_step"],
+                "n_gpus": args.gpus, "steps": res["steps"], "warmup": 16, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "cpu_baseline": res,
-                "e2e": {"value": res["value"], "unit": "anchor-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": res["value"], "unit": "anchor-ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "--steps / --warmup size the GPU arm; this arm times a bounded sample (median of 3 repeats of >= 2 s each, "
+                        "16 warm-up steps per thread) of the same workload with one anchor per host core"}
         emit(line)
         return
 
@@ -204,7 +340,7 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     A = args.anchors
 
-    def make_context(kind: str, decision_mode: str = "auto"):
+    def make_context(kind: str, decision_mode: str = "auto", graph_steps: int = STEPS_PER_GRAPH):
         syn, positions, forces, shells = build_workload(A, args.atoms, seed + 1000 * rank)
         if kind == "mmvt":
             integ = H.make_mmvt_integrator(syn, "")
@@ -219,9 +355,9 @@ def main() -> None:
         integ.setRandomNumberSeed(seed + rank)
         integ.setDecisionMode(decision_mode)
         integ.ringCapacity = 1 << 14
-        integ.setUseGraph(True, STEPS_PER_GRAPH)
+        integ.setUseGraph(graph_steps >= 4, max(4, graph_steps))
         ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=A,
-                         randomPoolSteps=STEPS_PER_GRAPH)
+                         randomPoolSteps=max(4, graph_steps))
         ctx.setPositions(positions)
         ctx.setVelocities(syn.velocities)
         f = np.zeros((3, ctx.padded_num_atoms), dtype=np.int64)
@@ -231,8 +367,10 @@ def main() -> None:
         return ctx, integ, f
 
     def timed_run(ctx, integ, steps, warmup, sampler=None):
-        """Returns (ms total, ms spent inside step-graph replays, launches)."""
+        """Returns (ms total, ms spent inside the step launches, launches, clocks, eager launches).  Steps run as replays of the
+        integrator's step graph (integ.stepsPerGraph steps each); what does not fill a graph is launched eagerly and counted."""
         stream = ctx.stream
+        g = integ.stepsPerGraph // 4 * 4 if integ.useGraph else 0
         integ.step(warmup)
         if world > 1:
             dist.barrier()
@@ -241,16 +379,16 @@ def main() -> None:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pairs = []
-        done = 0
+        done = eager = 0
         with torch.cuda.stream(stream):
             ev0.record(stream)
             integ._update_params()
             while done < steps:
-                n = min(STEPS_PER_GRAPH, steps - done)
-                ri = integ._prepare_random(n)                      # Philox refill when the pool is exhausted
+                n = g if (g and steps - done >= g) else min(steps - done, g - 1 if g else steps - done)
+                ri = integ._prepare_random(n)                      # Philox refill when a pool is in use and exhausted
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                if n == STEPS_PER_GRAPH:
+                if n == g:
                     key = (ri, ctx.random.data_ptr() if ctx.random is not None else 0, integ._prev, integ._steps_issued % 4)
                     if integ._graph_key != key:
                         raise RuntimeError("graph must be warm before the timed region")
@@ -259,9 +397,11 @@ def main() -> None:
                     bufs = ctx.buffers()
                     for s in range(n):
                         L.check(L.lib.seekr2_b200_step(integ._handle, C.byref(bufs), ri + s * ctx.padded_num_atoms, ctx.stream_ptr))
+                    eager += n
                 b.record(stream)
                 pairs.append((a, b, n))
                 ctx.random_cursor += n
+                integ._steps_issued += n
                 done += n
             ev1.record(stream)
         torch.cuda.synchronize()
@@ -270,12 +410,12 @@ def main() -> None:
         clocks = sampler.stop() if sampler else None
         total = ev0.elapsed_time(ev1)
         kernel_ms = sum(a.elapsed_time(b) for a, b, _ in pairs)
-        return total, kernel_ms, sum(n for _, _, n in pairs), clocks
+        return total, kernel_ms, sum(n for _, _, n in pairs), clocks, eager
 
     # ---- device-resident throughput (value) ---------------------------------------------------------
-    ctx, integ, fhost = make_context("mmvt")
+    ctx, integ, fhost = make_context("mmvt", graph_steps=G)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    total_ms, kernel_ms, launches, clocks = timed_run(ctx, integ, args.steps, W, sampler)
+    total_ms, kernel_ms, launches, clocks, eager_launches = timed_run(ctx, integ, args.steps, W, sampler)
     fills = 0   # no pool-fill launches: the step kernel generates its Gaussian numbers
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
@@ -303,57 +443,79 @@ def main() -> None:
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this very
     # workload (profiles/r01d_fused_step_ncu_full.txt: 260.2 MB read + 132.9 MB written; the tail of the writes is
     # still in L2 when the kernel ends); null otherwise
-    traffic = 393.1e6 if (A, args.atoms) == (128, N_ATOMS) else None
+    traffic, traffic_source = ncu_traffic(A, args.atoms)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fused_step_kernel<MIXED,MMVT>" if integ.getDecisionMode() == "handoff" else "fused_local_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
+                "traffic": traffic, "traffic_source": traffic_source, "kernel": "fused_step_kernel<MIXED,MMVT>" if integ.getDecisionMode() == "handoff" else "fused_local_kernel<MIXED,MMVT>", "us_per_launch": per_launch_s * 1e6,
                 "algorithmic_bytes_per_launch": atoms_per_launch * BYTES_PER_ATOM_STEP,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback"}
 
     # ---- plain Langevin comparator (north star: fused MMVT step <= 1.05 x plain Langevin step) -----
-    ctx_l, integ_l, _ = make_context("langevin")
-    l_total, l_kernel, l_launches, _ = timed_run(ctx_l, integ_l, args.steps, W)
+    ctx_l, integ_l, _ = make_context("langevin", graph_steps=G)
+    l_total, l_kernel, l_launches, _, _ = timed_run(ctx_l, integ_l, args.steps, W)
     mmvt_over_langevin = (kernel_ms / launches) / (l_kernel / l_launches)
     del ctx_l, integ_l
 
+    # ---- the same two kernels over a long run (own fixed step count, whole 32-step graphs): the driver's --steps may be a
+    #      millisecond's worth of launches; this shows what the headline converges to ----
+    long_steps = 2048
+    ctx_x, integ_x, _ = make_context("mmvt")
+    xt, xk, xn, _, _ = timed_run(ctx_x, integ_x, long_steps, STEPS_PER_GRAPH)
+    del ctx_x, integ_x
+    ctx_x, integ_x, _ = make_context("langevin")
+    _, xlk, xln, _, _ = timed_run(ctx_x, integ_x, long_steps, STEPS_PER_GRAPH)
+    del ctx_x, integ_x
+    if world > 1:
+        t = torch.tensor([xt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        xt = float(t.item())
+    long_run = {"steps": long_steps, "steps_per_graph": STEPS_PER_GRAPH, "launch_mode": "cuda graph replay",
+                "value": ns_per_day(long_steps / (xt * 1e-3)) * A * world, "unit": "anchor-ns/day",
+                "us_per_launch": xk / xn * 1e3, "roofline_frac": atoms_per_launch * BYTES_PER_ATOM_STEP / (xk * 1e-3 / xn) / 1e9 / peak,
+                "plain_langevin_us_per_launch": xlk / xln * 1e3, "mmvt_over_plain_langevin": (xk / xn) / (xlk / xln)}
+
     # ---- the other integrators of the plugin on the same buffers (BASELINE.json configs[2]) --
-    variants = {"mmvt": kernel_ms / launches * 1e3, "langevin": l_kernel / l_launches * 1e3}
-    v_steps = max(STEPS_PER_GRAPH, min(args.steps, 512) // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
+    variants = {"mmvt": long_run["us_per_launch"], "langevin": long_run["plain_langevin_us_per_launch"]}
+    v_steps = 512
     for kind in ("mmvt_middle", "elber", "elber_middle"):
         ctx_v, integ_v, _ = make_context(kind)
-        _, kv, nv, _ = timed_run(ctx_v, integ_v, v_steps, W)
+        _, kv, nv, _, _ = timed_run(ctx_v, integ_v, v_steps, STEPS_PER_GRAPH)
         variants[kind] = kv / nv * 1e3
         del ctx_v, integ_v
 
     # ---- latency mode: ONE anchor per GPU (the literal "8 anchors one per GPU" configuration) ------
     A_saved, A = A, 1
+    LS, LW = LATENCY_STEPS, 4 * STEPS_PER_GRAPH
+    graphs_note = f"{LS} steps timed as {LS // STEPS_PER_GRAPH} replays of a {STEPS_PER_GRAPH}-step CUDA graph (fixed, independent of --steps), after {LW} warm-up steps"
     ctx1, integ1, _ = make_context("mmvt")
-    t1, k1, n1, _ = timed_run(ctx1, integ1, args.steps, W)
+    t1, k1, n1, _, e1 = timed_run(ctx1, integ1, LS, LW)
     mode1 = integ1.getDecisionMode()
     del ctx1, integ1
     ctx1, integ1, _ = make_context("langevin")
-    t1l, k1l, n1l, _ = timed_run(ctx1, integ1, args.steps, W)
+    t1l, k1l, n1l, _, _ = timed_run(ctx1, integ1, LS, LW)
     del ctx1, integ1
     ctx1, integ1, _ = make_context("mmvt", decision_mode="handoff")
-    t1h, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    t1h, _, _, _, _ = timed_run(ctx1, integ1, LS, LW)
     del ctx1, integ1
-    single_anchor = {"ns_per_day_per_anchor": ns_per_day(args.steps / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / args.steps,
-                     "plain_langevin_us_per_step": t1l * 1e3 / args.steps, "mmvt_over_plain_langevin": t1 / t1l,
-                     "decision_mode": mode1, "us_per_step_handoff_mode": t1h * 1e3 / args.steps,
+    single_anchor = {"ns_per_day_per_anchor": ns_per_day(LS / (t1 * 1e-3)), "us_per_step": t1 * 1e3 / LS,
+                     "plain_langevin_us_per_step": t1l * 1e3 / LS, "mmvt_over_plain_langevin": t1 / t1l,
+                     "decision_mode": mode1, "us_per_step_handoff_mode": t1h * 1e3 / LS,
+                     "steps": LS, "warmup": LW, "steps_per_graph": STEPS_PER_GRAPH, "eager_launches": e1,
+                     "launch_mode": "cuda graph replay" if e1 == 0 else "mixed",
                      "note": "1 anchor per GPU, L2-resident, launch-latency bound; LOCAL decision mode (every block evaluates the "
                              "boundaries in dedicated slot warps; the batched default workload above runs the decide-block hand-off); "
-                             "CUDA graph of 32 steps"}
+                             + graphs_note}
     # launch overhead per step: the same graphs on a 64-atom system (nothing to stream: what is left is the launch
     # itself and, for MMVT, the serial gather -> centroid -> decision -> store chain inside it)
     atoms_saved, args.atoms = args.atoms, 64
     ctx1, integ1, _ = make_context("mmvt")
-    t0m, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    t0m, _, _, _, _ = timed_run(ctx1, integ1, LS, LW)
     del ctx1, integ1
     ctx1, integ1, _ = make_context("langevin")
-    t0l, _, _, _ = timed_run(ctx1, integ1, args.steps, W)
+    t0l, _, _, _, _ = timed_run(ctx1, integ1, LS, LW)
     del ctx1, integ1
     args.atoms = atoms_saved
-    single_anchor["launch_overhead_us_per_step"] = {"mmvt": t0m * 1e3 / args.steps, "plain_langevin": t0l * 1e3 / args.steps,
-                                                    "note": "1 anchor x 64 atoms, CUDA graph of 32 steps"}
+    single_anchor["launch_overhead_us_per_step"] = {"mmvt": t0m * 1e3 / LS, "plain_langevin": t0l * 1e3 / LS, "steps": LS,
+                                                    "note": "1 anchor x 64 atoms; " + graphs_note}
     A = A_saved
 
     # ---- C2 / C3 (BASELINE.json configs[1], [2]): host-guest size, 2 520 atoms, host 147 / guest 15 atom centroid groups,
@@ -377,14 +539,15 @@ def main() -> None:
                            randomPoolSteps=STEPS_PER_GRAPH)
         ctx_h.setPositions(syn.positions)
         ctx_h.setVelocities(syn.velocities)
-        t, _, _, _ = timed_run(ctx_h, integ_h, args.steps, W)
+        t, _, _, _, _ = timed_run(ctx_h, integ_h, LS, LW)
         mode = integ_h.getDecisionMode()
-        return t * 1e3 / args.steps, mode
+        return t * 1e3 / LS, mode
     hg = {k: host_guest(k) for k in ("mmvt", "elber", "langevin")}
     host_guest_c2 = {"workload": "C2/C3 host-guest size: 2520 atoms, 147 + 15 atom centroid groups, spheres 0.3 / 0.5 nm, dt 2 fs, 1 anchor, mixed",
                      "mmvt_us_per_step": hg["mmvt"][0], "elber_us_per_step": hg["elber"][0], "plain_langevin_us_per_step": hg["langevin"][0],
                      "mmvt_ns_per_day": 86400.0 / (hg["mmvt"][0] * 1e-6) * 0.002e-3, "elber_ns_per_day": 86400.0 / (hg["elber"][0] * 1e-6) * 0.002e-3,
-                     "decision_mode": hg["mmvt"][1]}
+                     "mmvt_over_plain_langevin": hg["mmvt"][0] / hg["langevin"][0], "elber_over_plain_langevin": hg["elber"][0] / hg["langevin"][0],
+                     "decision_mode": hg["mmvt"][1], "steps": LS, "launch_mode": "cuda graph replay", "note": graphs_note}
 
     # ---- C5: synthetic 100 000-atom solvated box, 2 centroid-pair spheres + 4 axis planes (6 bits) ---
     box = None
@@ -402,8 +565,8 @@ def main() -> None:
         ctx_b = s2.Context(synb.system, integ_b, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=Ab)
         ctx_b.setPositions(synb.positions)
         ctx_b.setVelocities(synb.velocities)
-        b_steps = max(STEPS_PER_GRAPH, args.steps // 4 // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
-        tb, kb, nbl, _ = timed_run(ctx_b, integ_b, b_steps, W)
+        b_steps = 512
+        tb, kb, nbl, _, _ = timed_run(ctx_b, integ_b, b_steps, STEPS_PER_GRAPH)
         if world > 1:
             t = torch.tensor([tb], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -411,7 +574,7 @@ def main() -> None:
         per_launch = kb * 1e-3 / nbl
         box = {"workload": f"C5 box: {nb} atoms, {Ab} anchors per GPU, 2 centroid-pair spheres + 4 axis planes, dt 2 fs, mixed",
                "anchor_ns_per_day": b_steps / (tb * 1e-3) * 0.002e-3 * 86400.0 * Ab * world,
-               "us_per_launch": per_launch * 1e6,
+               "us_per_launch": per_launch * 1e6, "steps": b_steps, "launch_mode": "cuda graph replay",
                "achieved_gbs": Ab * nb * BYTES_PER_ATOM_STEP / per_launch / 1e9,
                "frac_of_hbm_peak": Ab * nb * BYTES_PER_ATOM_STEP / per_launch / 1e9 / peak}
         del ctx_b, integ_b
@@ -422,6 +585,7 @@ def main() -> None:
         # NUMA: allocate (first-touch) the pinned staging buffer and run the upload loop on the CPUs local to this GPU, where
         # the box says which they are; a buffer on the far socket costs a third of the PCIe rate
         old_affinity = None
+        staging_cpus = "all (no local_cpulist)"
         try:
             bus = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(torch.cuda.get_device_properties(dev), "pci_bus_id") else None
             dom = getattr(torch.cuda.get_device_properties(dev), "pci_domain_id", 0)
@@ -436,12 +600,13 @@ def main() -> None:
                 if cpus:
                     old_affinity = os.sched_getaffinity(0)
                     os.sched_setaffinity(0, cpus)
+                    staging_cpus = f"{len(cpus)} CPUs local to the GPU ({open(path).read().strip()})"
         except Exception:
             old_affinity = None
         pinned = torch.from_numpy(np.broadcast_to(fhost[None], (A,) + fhost.shape).copy()).pin_memory()
         integ.setUseGraph(False)
         h2d = pinned.numel() * 8
-        e_steps = max(8, min(args.steps, 192))
+        e_steps = 192                                               # fixed: ~0.25 s of PCIe traffic
 
         # double-buffered input: the upload of step k+1 (copy stream) runs under step k's launch, drain and host-side
         # collection; every step's force buffer still crosses PCIe from pinned host memory inside the timed region
@@ -488,8 +653,43 @@ def main() -> None:
             t = torch.tensor([e_dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_dt = float(t.item())
+        # e2e's own roofline: the H2D rate of the SAME pinned buffer into the SAME device buffer with nothing else going on,
+        # measured with this rank alone on the bus (ranks take turns) and with all ranks copying at once
+        def h2d_rate(copies=6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(copy_stream):
+                force_bufs[1].copy_(pinned, non_blocking=True)
+                a.record(copy_stream)
+                for _ in range(copies):
+                    force_bufs[1].copy_(pinned, non_blocking=True)
+                b.record(copy_stream)
+            torch.cuda.synchronize()
+            return h2d * copies / (a.elapsed_time(b) * 1e-3) / 1e9
+        alone = 0.0
+        for r in range(world):
+            if world > 1:
+                dist.barrier()
+            if r == rank:
+                alone = h2d_rate()
+        if world > 1:
+            dist.barrier()
+        together = h2d_rate()
+        rates = torch.tensor([alone, together], device=dev, dtype=torch.float64)
+        if world > 1:
+            all_rates = [torch.zeros_like(rates) for _ in range(world)]
+            dist.all_gather(all_rates, rates)
+        else:
+            all_rates = [rates]
+        alone_all = [float(t[0]) for t in all_rates]
+        together_all = [float(t[1]) for t in all_rates]
+        step_gbs = h2d / (e_dt / e_steps) / 1e9                   # what the slowest rank's e2e step moved per second
         e2e = {"value": ns_per_day(e_steps / e_dt) * A * world, "unit": "anchor-ns/day", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": e_dt / e_steps * 1e3,
+               "h2d_gbs_per_gpu": step_gbs,
+               "pcie_ceiling_gbs": {"alone_per_gpu": alone_all, "all_ranks_at_once_per_gpu": together_all,
+                                    "all_ranks_at_once_aggregate": sum(together_all),
+                                    "how": f"cudaMemcpyAsync of the same {h2d / 1e6:.1f} MB pinned buffer, 6 copies back to back, CUDA events; ranks one after the other, then all together"},
+               "frac_of_pcie": step_gbs / min(together_all), "staging_cpus": staging_cpus,
                "note": "integrator.step(1) per step: H2D of the step's force buffer from pinned host memory (double-buffered: the next step's upload runs under this step), one fused launch, the step's crossing records drained to pinned host memory and appended to the integrator's record list; PCIe-bound by the force upload"}
 
     # ---- the call a user of the reference makes: context.setPositions / setVelocities, integrator.step(n) with a
@@ -504,7 +704,7 @@ def main() -> None:
         integ_t.ringCapacity = 1 << 14
         integ_t.setUseGraph(True, STEPS_PER_GRAPH)
         ctx_t = s2.Context(syn_t.system, integ_t, {"CudaPrecision": "mixed", "CudaDeviceIndex": local_rank}, numAnchors=A)
-        n_call = max(STEPS_PER_GRAPH, min(args.steps, 1024) // STEPS_PER_GRAPH * STEPS_PER_GRAPH)
+        n_call = 1024                                               # fixed: the call's set / get traffic is amortised over it
 
         def call():
             ctx_t.setPositions(positions_t)
@@ -530,18 +730,27 @@ def main() -> None:
                             "(2 launches per step, CUDA graph) + getState(positions, velocities) (D2H), wall clock"}
         del ctx_t, integ_t, state
 
+    # ---- the drop-in seam itself: the reference's integrator classes stepping through platforms/b200 (our adapter) and through
+    #      the reference's own CUDA platform (CudaSeekr2Kernels.cpp, unmodified), both under the OpenMM stand-in ----
+    adapter = None
+    if rank == 0 and world == 1 and not args.no_adapter:
+        torch.cuda.synchronize()
+        adapter = adapter_vs_reference(seed)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(1, args.cpu_steps or 32000, 16, args.atoms, seed)   # ~12 s at ~0.38 ms per anchor-step
+        cpu = cpu_reference(args.atoms, seed)                     # 2 x 3 repeats of >= 2 s
 
     if rank == 0:
         line = {"metric": "mmvt_aggregate_anchor_ns_per_day", "value": value, "unit": "anchor-ns/day", "n_gpus": world,
                 "steps": args.steps, "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 positions + f32 correction, f64 velocities (CudaPrecision=mixed)",
+                "data": "synthetic", "config": config, "long_run": long_run, "eager_launches": eager_launches,
                 "ns_per_day_per_anchor": value / (A * world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches + fills, "roofline": roofline, "cpu_baseline": cpu,
                 "mmvt_over_plain_langevin": mmvt_over_langevin, "us_per_launch_by_integrator": variants,
                 "single_anchor_per_gpu": single_anchor, "host_guest_c2": host_guest_c2, "box_100k": box, "api_call": api_call,
+                "adapter_vs_reference_cuda_platform": adapter,
                 "bounce_steps": bounces, "crossing_records": records, "gathered_anchors": gathered,
                 "precision": "mixed (f32 positions + f32 correction, f64 velocities)"}
         emit(line)

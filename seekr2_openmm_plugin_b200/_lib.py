@@ -165,7 +165,16 @@ def _load() -> C.CDLL:
     return lib
 
 
-lib = _load()
+class _StructsOnly:
+    """SEEKR2_B200_STRUCTS_ONLY=1 (bench.py --impl reference, the CPU arm): the process wants the struct definitions of the
+    ABI and must NOT load the product library, so that the driver's record of loaded .so files shows a clean CPU arm.
+    Any attempt to call into the library fails loudly."""
+
+    def __getattr__(self, name):
+        raise ImportError(f"libseekr2_b200.so was deliberately not loaded (SEEKR2_B200_STRUCTS_ONLY=1): {name} is unavailable")
+
+
+lib = _StructsOnly() if os.environ.get("SEEKR2_B200_STRUCTS_ONLY") == "1" else _load()
 
 
 def check(rc: int) -> None:

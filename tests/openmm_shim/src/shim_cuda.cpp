@@ -365,6 +365,11 @@ int CudaIntegrationUtilities::prepareRandomNumbers(int numValues) {
         return oldPos;
     }
     if (numValues > (int) random.getSize()) throw OpenMMException("openmm_shim: random pool too small");
+    /* timing runs (bench.py's adapter leg): OPENMM_SHIM_REUSE_POOL=1 fills the pool once and then wraps around -- OpenMM
+       refills it with a GPU kernel, this stand-in with a host loop over 32 x paddedNumAtoms normals that would swamp the
+       integrator kernels being timed */
+    static const bool reuse = [] { const char* r = std::getenv("OPENMM_SHIM_REUSE_POOL"); return r && r[0] == '1'; }();
+    if (reuse && shimPoolFills > 0) { randomPos = numValues; return 0; }
     std::vector<float> pool(4 * random.getSize());
     if (randomSource()) {
         randomSource()(pool.data(), random.getSize(), shimPoolFills);
