@@ -257,9 +257,11 @@ int seekr2_b200_get_params(seekr2_b200_handle h, double out_vscale_fscale_noises
 
 /* replaces integration.initRandomNumberGenerator(seed) (CudaSeekr2Kernels.cpp:109,396) for callers
    that pass d_random == NULL: the step kernels then generate their Gaussian numbers themselves
-   (Philox4x32-10 keyed by `seed`, counter = (atom, anchor_base + anchor, step)) instead of reading
-   OpenMM's pool.  anchor_base makes the streams of different ranks distinct.                        */
-int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base);
+   (Philox4x32-10 keyed by `seed`, counter = (atom, anchor_base + anchor * anchor_id_stride, step)) instead of reading
+   OpenMM's pool.  The counter's anchor word must be the GLOBAL anchor id, so that one seed serves all ranks without two
+   anchors sharing a stream: anchors dealt round-robin -> anchor_base = rank, anchor_id_stride = world size; contiguous
+   blocks -> anchor_base = first anchor of the rank, anchor_id_stride = 1 (0 is read as 1).                    */
+int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base, uint32_t anchor_id_stride);
 
 /* ---- state the kernels need besides OpenMM's buffers ---------------------------------------- */
 
@@ -413,10 +415,10 @@ int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t
                                    const double* d_bond_params /* [nb][2] = r0,k */,
                                    long long* d_force, void* stream);
 /* fill a Gaussian pool with exactly the numbers the in-kernel generator would use:
-   pool[a*anchor_stride + s*padded + i] = N(seed; atom i, anchor anchor_base + a, step step0 + s)   */
+   pool[a*anchor_stride + s*padded + i] = N(seed; atom i, anchor anchor_base + a*anchor_id_stride, step step0 + s)   */
 int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t padded_num_atoms,
                                   int64_t anchor_stride, int32_t num_steps, uint64_t seed,
-                                  uint32_t anchor_base, uint64_t step0, void* stream);
+                                  uint32_t anchor_base, uint32_t anchor_id_stride, uint64_t step0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,8 @@ struct EngineDev {
     long long* step_shadow;      // [4][A] step index of the fused launch with that phase (launch count mod 4): launch k reads
                                  // phase k, writes phase k+2 -- stable during the launch and already final when launch k starts early (PDL)
     unsigned long long rng_seed; // in-kernel Philox key (used when the caller passes no random pool)
-    unsigned rng_anchor_base;    // global index of this engine's first anchor (distinct streams per rank)
+    unsigned rng_anchor_base;    // Philox stream of local anchor a = rng_anchor_base + a * rng_anchor_stride: the GLOBAL anchor id, whatever
+    unsigned rng_anchor_stride;  // way anchors are dealt to ranks (round-robin: base = rank, stride = world size; blocks: base = first, stride 1)
     long long* probe;            // optional timing probe (debug, seekr2_b200_debug_set_probe)
     long long* hint;             // mapped pinned host memory [2][A]: ring head, clock resets -- written when they change (seekr2_b200_poll)
     int* head_start;             // [2] decide blocks that have issued their gathers (per launch parity)

@@ -540,7 +540,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.slot_atom = h->d_slot_atom; d.slot_group = h->d_slot_group; d.slot_weight = h->d_slot_weight;
     d.boundaries = h->d_boundaries; d.state = h->d_state; d.ring = h->d_ring; d.slab = h->d_slab;
     d.decision = h->d_decision; d.flags = h->d_flags; d.step_shadow = h->d_step_shadow;
-    d.rng_seed = 0; d.rng_anchor_base = 0; d.probe = nullptr;
+    d.rng_seed = 0; d.rng_anchor_base = 0; d.rng_anchor_stride = 1; d.probe = nullptr;
     d.snap_slots = snap_slots;
     if (d.snap_slots > 0) {
         if (d.snap_slots >= (1 << 20)) return bail(fail(SEEKR2_B200_ERR_INVALID, "too many save_state_slots"));
@@ -581,11 +581,12 @@ int seekr2_b200_set_params(seekr2_b200_handle h, double temperature, double fric
     return SEEKR2_B200_OK;
 }
 
-int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base) {
+int seekr2_b200_set_rng(seekr2_b200_handle h, uint64_t seed, uint32_t anchor_base, uint32_t anchor_id_stride) {
     if (!h) return fail(SEEKR2_B200_ERR_INVALID, "null engine handle");
     if (h->capturing) return fail(SEEKR2_B200_ERR_INVALID, "the RNG cannot change inside a graph capture");
     h->dev.rng_seed = seed;
     h->dev.rng_anchor_base = anchor_base;
+    h->dev.rng_anchor_stride = anchor_id_stride ? anchor_id_stride : 1;
     return SEEKR2_B200_OK;
 }
 
@@ -1016,12 +1017,12 @@ int seekr2_b200_harness_bond_force(int32_t precision, int32_t num_atoms, int32_t
 }
 
 int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t padded, int64_t anchor_stride,
-                                  int32_t num_steps, uint64_t seed, uint32_t anchor_base, uint64_t step0, void* stream) {
+                                  int32_t num_steps, uint64_t seed, uint32_t anchor_base, uint32_t anchor_id_stride, uint64_t step0, void* stream) {
     if (!d_random || num_anchors < 1 || padded < 1 || num_steps < 0 || anchor_stride < (int64_t) num_steps * padded)
         return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
     if (num_steps == 0) return SEEKR2_B200_OK;
     dim3 grid((unsigned) ((padded + kThreads - 1) / kThreads), (unsigned) num_anchors, (unsigned) (num_steps < 32 ? num_steps : 32));
-    fill_pool_kernel<<<grid, kThreads, 0, (cudaStream_t) stream>>>((float4*) d_random, padded, anchor_stride, num_steps, seed, anchor_base, step0);
+    fill_pool_kernel<<<grid, kThreads, 0, (cudaStream_t) stream>>>((float4*) d_random, padded, anchor_stride, num_steps, seed, anchor_base, anchor_id_stride ? anchor_id_stride : 1, step0);
     CUDA_TRY(cudaGetLastError());
     return SEEKR2_B200_OK;
 }

@@ -52,7 +52,8 @@ class _B200LangevinBase:
         self.saveStateSlots = 32       # crossing states kept on the device between drains (saveStateFileName set)
         self.drainInterval = 4096      # steps between asynchronous drains inside one step(n) call
         self.useRandomPool = False     # True: Gaussian pool refilled by a harness kernel (OpenMM style)
-        self.rngAnchorBase = 0         # global index of the context's first anchor (multi-GPU runs)
+        self.rngAnchorBase = 0         # Philox stream of local anchor a = rngAnchorBase + a * rngAnchorStride = its GLOBAL id
+        self.rngAnchorStride = 1       # (multi-GPU, anchors dealt round-robin: base = rank, stride = world size)
         self._steps_issued = 0
         self._prev = (None, None, None)
         self._graph_key = None
@@ -152,7 +153,7 @@ class _B200LangevinBase:
             L.lib.seekr2_b200_destroy(self._handle)
             self._handle = C.c_void_p()
         L.check(L.lib.seekr2_b200_create(C.byref(cfg), C.byref(self._handle)))
-        L.check(L.lib.seekr2_b200_set_rng(self._handle, self.randomNumberSeed, self.rngAnchorBase))
+        L.check(L.lib.seekr2_b200_set_rng(self._handle, self.randomNumberSeed, self.rngAnchorBase, self.rngAnchorStride))
         self._steps_issued = 0
         self._prev = (None, None, None)
         self._graph_key = None
@@ -213,7 +214,7 @@ class _B200LangevinBase:
             if ctx.random_injected:
                 raise L.Seekr2Error(L.ERR_INVALID, "injected random pool exhausted")
             L.check(L.lib.seekr2_b200_harness_fill_pool(ctx.random.data_ptr(), ctx.num_anchors, Np, int(ctx.random.shape[1]),
-                                                        ctx.random_pool_steps, self.randomNumberSeed, self.rngAnchorBase,
+                                                        ctx.random_pool_steps, self.randomNumberSeed, self.rngAnchorBase, self.rngAnchorStride,
                                                         self._steps_issued, ctx.stream_ptr))
             ctx.random_cursor = 0
         return ctx.random_cursor * Np

@@ -40,18 +40,25 @@ def unpack_row(row: np.ndarray) -> Dict:
 
 
 def gather_rows(local_rows: np.ndarray, world_size: int, device=None) -> np.ndarray:
-    """all_gather of equally shaped [n_local, STAT_WIDTH] float64 blocks; returns rows sorted by anchor."""
+    """all_gather of [n_local, STAT_WIDTH] float64 blocks; returns rows sorted by anchor.  Ranks may hold different numbers
+    of anchors (round-robin leaves the last ranks one short when num_anchors % world_size != 0): blocks are padded to the
+    largest count with rows of anchor id -1, which are dropped after the gather."""
     if world_size <= 1:
         out = local_rows
     else:
         import torch
         import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(local_rows))
+        count = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=device)
+        dist.all_reduce(count, op=dist.ReduceOp.MAX)
+        padded = np.full((int(count.item()), STAT_WIDTH), -1.0, dtype=np.float64)
+        padded[: local_rows.shape[0]] = local_rows
+        t = torch.from_numpy(padded)
         if device is not None:
             t = t.to(device)
         parts = [torch.empty_like(t) for _ in range(world_size)]
         dist.all_gather(parts, t)
         out = torch.cat(parts).cpu().numpy()
+        out = out[out[:, 0] >= 0]
     return out[np.argsort(out[:, 0], kind="stable")]
 
 

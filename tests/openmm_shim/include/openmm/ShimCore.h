@@ -71,6 +71,9 @@ public:
     virtual bool usesPeriodicBoundaryConditions() const { return false; }
     /* shim: energy of this force at `positions`; adds the forces to `forces` when it is not NULL */
     virtual double shimEvaluate(const std::vector<Vec3>& positions, const std::vector<double>& masses, std::vector<Vec3>* forces) const = 0;
+    /* shim: true if the ENERGY depends on the listed particles only (appended to `particles`); lets an energy-only pass of
+       a force group fetch those positions instead of all of them */
+    virtual bool shimEnergyParticles(std::vector<int>& particles) const { return false; }
 private:
     int forceGroup;
 };
@@ -122,6 +125,10 @@ public:
     void setUsesPeriodicBoundaryConditions(bool periodic) { usePeriodic = periodic; }
     bool usesPeriodicBoundaryConditions() const { return usePeriodic; }
     double shimEvaluate(const std::vector<Vec3>&, const std::vector<double>&, std::vector<Vec3>*) const;
+    bool shimEnergyParticles(std::vector<int>& particles) const {
+        for (const Group& g : groups) particles.insert(particles.end(), g.particles.begin(), g.particles.end());
+        return true;
+    }
 private:
     struct Group { std::vector<int> particles; std::vector<double> weights; };
     struct Bond { std::vector<int> groups; std::vector<double> parameters; };
@@ -334,6 +341,8 @@ public:
     virtual long long getStepCount() const = 0;
     virtual void getPositions(std::vector<Vec3>& positions) = 0;             /* as Context::getState returns them */
     virtual void getForcePositions(std::vector<Vec3>& positions) = 0;        /* what force kernels read */
+    /* the same for the listed particles only (entries of the others are left alone); false = not supported, fetch all */
+    virtual bool getForcePositionsOf(const std::vector<int>& particles, std::vector<Vec3>& positions) { return false; }
     virtual void setPositions(const std::vector<Vec3>& positions) = 0;
     virtual void getVelocities(std::vector<Vec3>& velocities) = 0;
     virtual void setVelocities(const std::vector<Vec3>& velocities) = 0;
@@ -364,6 +373,9 @@ public:
     /* shim */
     ShimPlatformContext* shimContext;
     long long shimForceEvaluations, shimEnergyEvaluations;
+    std::map<int, std::vector<int> > shimEnergySubsets;     /* force-group mask -> particles its energy depends on ({-1} = all) */
+    std::vector<Vec3> shimPositions;
+    std::vector<double> shimMasses;
     long long shimForceNs, shimEnergyNs;        /* host time spent in force passes / energy-only passes */
     double calcKineticEnergy() { return integrator.computeKineticEnergy(); }   /* OpenMM: ContextImpl::calcKineticEnergy() */
 private:

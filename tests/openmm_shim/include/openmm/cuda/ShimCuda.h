@@ -137,6 +137,7 @@ public:
     /* ShimPlatformContext */
     void getPositions(std::vector<Vec3>& positions);
     void getForcePositions(std::vector<Vec3>& positions);
+    bool getForcePositionsOf(const std::vector<int>& particles, std::vector<Vec3>& positions);
     void setPositions(const std::vector<Vec3>& positions);
     void getVelocities(std::vector<Vec3>& velocities);
     void setVelocities(const std::vector<Vec3>& velocities);
@@ -152,6 +153,11 @@ public:
 private:
     int at(int particle) const { return indexOfAtom[particle]; }
     std::vector<int> indexOfAtom;            /* inverse of atomIndex */
+    /* gather of a few positions for energy-only passes (getForcePositionsOf) */
+    CudaArray gatherIndex, gatherOut;
+    std::vector<int> gatherParticles;
+    long long gatherReorders = -1;
+    CUfunction gatherKernel = 0;
     int reorderEvery, reorderCalls;
     const System& system;
     CudaPlatform::PlatformData& platformData;

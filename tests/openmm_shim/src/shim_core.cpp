@@ -5,6 +5,7 @@
 #include "openmm/internal/AssertionUtilities.h"
 #include "openmm/reference/SimTKOpenMMRealType.h"
 #include "openmm/serialization/XmlSerializer.h"
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cctype>
@@ -367,11 +368,38 @@ double ContextImpl::calcForcesAndEnergy(bool includeForces, bool includeEnergy, 
         const std::chrono::steady_clock::time_point t0; long long& into;
         ~Timer() { into += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
     } timer{t0, includeForces ? shimForceNs : shimEnergyNs};
-    std::vector<Vec3> x;
-    shimContext->getForcePositions(x);
-    std::vector<double> masses(system.getNumParticles());
-    for (int i = 0; i < system.getNumParticles(); i++) masses[i] = system.getParticleMass(i);
-    std::vector<Vec3> f(x.size());
+    /* Energy-only pass of a few force groups (what the reference's kernels ask for every step, CudaSeekr2Kernels.cpp:248,
+       :527,:552): when every Force in the mask says which particles its energy depends on, only those positions are fetched
+       from the device (one small gather kernel + one small blocking copy -- the shape of what OpenMM does: a few small kernels
+       and a blocking read-back of the energy) instead of the whole position array. */
+    std::vector<Vec3>& x = shimPositions;
+    if (shimMasses.size() != (size_t) system.getNumParticles()) {
+        shimMasses.resize(system.getNumParticles());
+        for (int i = 0; i < system.getNumParticles(); i++) shimMasses[i] = system.getParticleMass(i);
+    }
+    const std::vector<double>& masses = shimMasses;
+    bool fetched = false;
+    if (!includeForces) {
+        auto it = shimEnergySubsets.find(groups);
+        if (it == shimEnergySubsets.end()) {
+            std::vector<int> subset;
+            bool all = false;
+            for (int i = 0; i < system.getNumForces() && !all; i++) {
+                const Force& force = system.getForce(i);
+                if (((groups >> force.getForceGroup()) & 1) && !force.shimEnergyParticles(subset)) all = true;
+            }
+            std::sort(subset.begin(), subset.end());
+            subset.erase(std::unique(subset.begin(), subset.end()), subset.end());
+            if (all) subset.assign(1, -1);
+            it = shimEnergySubsets.emplace(groups, subset).first;
+        }
+        if (it->second.empty() || it->second[0] >= 0) {
+            x.resize(system.getNumParticles());
+            fetched = it->second.empty() || shimContext->getForcePositionsOf(it->second, x);
+        }
+    }
+    if (!fetched) shimContext->getForcePositions(x);
+    std::vector<Vec3> f(includeForces ? x.size() : 0);
     double energy = 0;
     for (int i = 0; i < system.getNumForces(); i++) {
         const Force& force = system.getForce(i);

@@ -221,6 +221,43 @@ void CudaContext::getForcePositions(std::vector<Vec3>& positions) {
         for (int i = 0; i < numAtoms; i++) positions[i] = Vec3(p[4 * at(i)], p[4 * at(i) + 1], p[4 * at(i) + 2]);
     }
 }
+bool CudaContext::getForcePositionsOf(const std::vector<int>& particles, std::vector<Vec3>& positions) {
+    const int n = (int) particles.size();
+    if (n == 0) return true;
+    setAsCurrent();
+    if (!gatherKernel) {
+        CUmodule module = createModule("extern \"C\" __global__ void shimGather(const real4* __restrict__ posq, const int* __restrict__ index, int n, real4* __restrict__ out) {\n"
+                                       "    const int i = blockIdx.x * blockDim.x + threadIdx.x;\n    if (i < n) out[i] = posq[index[i]];\n}\n");
+        gatherKernel = getKernel(module, "shimGather");
+    }
+    if (particles != gatherParticles || gatherReorders != shimReorders) {          /* (re)build the index list */
+        if (!gatherIndex.isInitialized() || gatherIndex.getSize() < (size_t) n) {
+            if (gatherIndex.isInitialized()) return false;                         /* one subset size per context is enough here */
+            gatherIndex.initialize(*this, n, sizeof(int), "shimGatherIndex");
+            gatherOut.initialize(*this, n, useDouble ? 32 : 16, "shimGatherOut");
+        }
+        if (gatherIndex.getSize() != (size_t) n) return false;
+        std::vector<int> index(n);
+        for (int i = 0; i < n; i++) index[i] = at(particles[i]);
+        gatherIndex.upload(index.data());
+        gatherParticles = particles;
+        gatherReorders = shimReorders;
+    }
+    int count = n;
+    void* args[] = {&posq.getDevicePointer(), &gatherIndex.getDevicePointer(), &count, &gatherOut.getDevicePointer()};
+    const CUresult r = cuLaunchKernel(gatherKernel, (n + 63) / 64, 1, 1, 64, 1, 1, 0, stream, args, NULL);
+    if (r != CUDA_SUCCESS) throw OpenMMException("Error invoking shimGather: " + getErrorString(r));
+    if (useDouble) {
+        std::vector<double> p(4 * (size_t) n);
+        gatherOut.download(p.data());
+        for (int i = 0; i < n; i++) positions[particles[i]] = Vec3(p[4 * i], p[4 * i + 1], p[4 * i + 2]);
+    } else {
+        std::vector<float> p(4 * (size_t) n);
+        gatherOut.download(p.data());
+        for (int i = 0; i < n; i++) positions[particles[i]] = Vec3(p[4 * i], p[4 * i + 1], p[4 * i + 2]);
+    }
+    return true;
+}
 void CudaContext::getPositions(std::vector<Vec3>& positions) {
     getForcePositions(positions);
     if (useMixed) {

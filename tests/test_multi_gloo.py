@@ -32,7 +32,7 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    mine = multi.partition_anchors(6, world, rank)
+    mine = multi.partition_anchors(7, world, rank)                  # uneven: rank 0 holds 4 anchors, rank 1 holds 3
     rows = np.stack([multi.pack_state(a, _fake_state(a)) for a in mine])
     merged = multi.gather_rows(rows, world)
     np.save(os.path.join(out_dir, f"merged{rank}.npy"), merged)
@@ -44,7 +44,7 @@ def test_gather_statistics_world_size_2(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     m0, m1 = np.load(tmp_path / "merged0.npy"), np.load(tmp_path / "merged1.npy")
     np.testing.assert_array_equal(m0, m1)                       # every rank ends with the same table
-    assert list(m0[:, 0]) == [0, 1, 2, 3, 4, 5]                 # sorted by global anchor id
+    assert list(m0[:, 0]) == [0, 1, 2, 3, 4, 5, 6]              # sorted by global anchor id, padding rows dropped
     for a, row in enumerate(m0):
         d = multi.unpack_row(row)
         assert (d["anchor"], d["steps"], d["bounce_counter"], d["records"]) == (a, 100 + a, a, 2 * a)
@@ -56,3 +56,19 @@ def test_single_rank_gather_is_identity():
     rows = np.stack([multi.pack_state(a, _fake_state(a)) for a in (2, 0, 1)])
     merged = multi.gather_rows(rows, 1)
     assert list(merged[:, 0]) == [0, 1, 2]
+
+
+def test_rng_streams_are_keyed_by_the_global_anchor_id():
+    """One seed for the whole job: local anchor j of rank r (round-robin) must draw from stream r + j * world -- the global
+    anchor id -- so that no two anchors of the job share a stream (base + j alone collides: rank 0 local 1 == rank 1 local 0)."""
+    world, n = 4, 13
+    seen = {}
+    for rank in range(world):
+        mine = multi.partition_anchors(n, world, rank)
+        base, stride = rank, world                                 # what bench.py sets on the integrator
+        for j, a in enumerate(mine):
+            stream = base + j * stride
+            assert stream == a
+            assert stream not in seen, (stream, seen[stream], (rank, j))
+            seen[stream] = (rank, j)
+    assert sorted(seen) == list(range(n))
