@@ -45,8 +45,12 @@ int fail(int code, const char* fmt, ...) {
 
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
-constexpr int kLocalBlocksPerSm = 4;           // auto mode: LOCAL decision when the streaming blocks number at most 4 x SMs (measured
-                                               // crossover on 23 036-atom anchors: LOCAL wins up to 6 anchors per GPU, the hand-off from 8)
+// auto mode (measured on 23 036-atom anchors, profiles/r02_local_regs_sweep.json; streaming blocks = anchors x ceil(atoms / 256)):
+//   up to  4 x SMs blocks (<= 6 anchors)   LOCAL decision, 96 registers, 256 streaming threads per block
+//   up to 12 x SMs blocks (<= 19 anchors)  LOCAL decision, 72 registers, 128 streaming threads per block
+//   up to 30 x SMs blocks (<= 49 anchors)  LOCAL decision, 72 registers, 256 streaming threads per block
+//   beyond                                 decide-block hand-off (HBM-bound: 48 registers, 1280 resident threads per SM)
+constexpr int kLocalBlocksPerSm = 30, kLocalLatencyBlocksPerSm = 4, kLocalSmallBlockBlocksPerSm = 12;
 constexpr long long kStageRecords = 1 << 16;   // staging buffer of the asynchronous drain (2.6 MB of mapped pinned memory)
 constexpr double kBoltzmann = 1.380649e-23;
 constexpr double kAvogadro = 6.02214076e23;
@@ -74,6 +78,7 @@ struct seekr2_b200_engine {
     bool slab_valid = false;
     bool use_pdl = true;            // fused step kernels are launched with programmatic stream serialization (SEEKR2_B200_PDL=0: off)
     bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
+    int local_regs = 96;            // LOCAL mode: register budget of the instantiation that runs (kLocalRegsLatency / kLocalRegsThroughput)
     int local_grid_x = 0;           // LOCAL mode: blocks per anchor (0 = not sized yet; sized at the first launch from the occupancy of the
                                     // instantiation that runs, so that the whole grid is resident at once)
     int sm_count = 0;
@@ -176,17 +181,37 @@ template <int P> int launch_gather(seekr2_b200_engine* h, const seekr2_b200_buff
     return SEEKR2_B200_OK;
 }
 
+template <int P, int KIND, int SCHEME, int REGS> int launch_local(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s, bool pdl);
+
 template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
     const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
     const bool pdl = h->use_pdl && !h->plain_next;
-    if (h->local_decide) {
+    if (h->local_decide)
+        return h->local_regs == kLocalRegsThroughput ? launch_local<P, KIND, SCHEME, kLocalRegsThroughput>(h, b, ri, s, pdl)
+                                                     : launch_local<P, KIND, SCHEME, kLocalRegsLatency>(h, b, ri, s, pdl);
+    const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid, 1, 1);
+    lc.blockDim = dim3(kThreads, 1, 1);
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase, bpa));
+    return SEEKR2_B200_OK;
+}
+
+template <int P, int KIND, int SCHEME, int REGS> int launch_local(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s, bool pdl) {
+    {
         // T streaming threads + the slot warps (none for plain Langevin)
         const int T = h->dev.local_stream_threads;
         const unsigned threads = (unsigned) T + (KIND == SEEKR2_B200_KIND_LANGEVIN ? 0u : (unsigned) h->dev.slot_threads);
         if (h->local_grid_x == 0) {
             // blocks per anchor: as many as are resident at once (each then walks ceil(tiles / G) tiles)
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_local_kernel<P, KIND, SCHEME>, (int) threads, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_local_kernel<P, KIND, SCHEME, REGS>, (int) threads, 0));
             long long resident = (long long) (per_sm > 0 ? per_sm : 1) * h->sm_count;
             if (const char* g = getenv("SEEKR2_B200_LOCAL_RESIDENT")) resident = atoll(g);                          // tuning knob
             long long gx = resident / h->cfg.num_anchors;
@@ -204,21 +229,9 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = attr;
         lc.numAttrs = pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase));
+        CUDA_TRY(cudaLaunchKernelEx(&lc, fused_local_kernel<P, KIND, SCHEME, REGS>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase));
         return SEEKR2_B200_OK;
     }
-    const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid, 1, 1);
-    lc.blockDim = dim3(kThreads, 1, 1);
-    lc.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr;
-    lc.numAttrs = pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&lc, fused_step_kernel<P, KIND, SCHEME>, h->dev, typed_bufs<P>(b), step_params<P>(h), h->step_size, ri, h->phase, bpa));
-    return SEEKR2_B200_OK;
 }
 
 template <int P> int launch_fused_kind(seekr2_b200_engine* h, const seekr2_b200_buffers* b, unsigned ri, cudaStream_t s) {
@@ -401,6 +414,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     // GPU, bound by latency and instruction issue; the decide-block hand-off is for batched, HBM-bound launches, where the
     // redundant slot warps and the larger register budget would cost bandwidth.
     bool local;
+    int local_threads = kThreads;
     {
         const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
         const bool eligible = snap_slots == 0 && aligned_slots <= kThreads;
@@ -417,6 +431,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             local = true;
         }
         h->local_decide = local;
+        // register budget and block size of the LOCAL kernel: latency regime (one round of tiles) vs throughput regime
+        const bool latency = stream_blocks <= (long long) prop.multiProcessorCount * kLocalLatencyBlocksPerSm;
+        h->local_regs = latency ? kLocalRegsLatency : kLocalRegsThroughput;
+        if (!latency && stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;
+        if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : kLocalRegsLatency;   // A/B knob
         if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
     }
 
@@ -451,7 +470,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     d.slot_layout = (packed || num_slots == 0) ? kLayoutPacked : kLayoutAligned;
     d.slot_threads = d.slot_layout == kLayoutPacked ? 32 : num_slots;
     {
-        int T = kThreads;
+        int T = local_threads;
         if (const char* lt = getenv("SEEKR2_B200_LOCAL_THREADS")) T = atoi(lt);                                      // tuning knob
         if (T < 32 || T > 512 || (T & 31)) return bail(fail(SEEKR2_B200_ERR_INVALID, "SEEKR2_B200_LOCAL_THREADS must be a multiple of 32 in [32, 512]"));
         d.local_stream_threads = T;

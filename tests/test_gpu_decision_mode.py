@@ -74,9 +74,13 @@ def test_auto_mode_picks_by_launch_size(cuda_device):
     integ = H.make_mmvt_integrator(syn, "")
     s2.Context(syn.system, integ, {"CudaPrecision": "mixed"})
     assert integ.getDecisionMode() == "local"
-    syn, positions = _shell_workload(64, 3000, H.SEED_BASE + 62)
+    syn, positions = _shell_workload(64, 3000, H.SEED_BASE + 62)       # 768 streaming blocks: several tiles per resident block
     integ = H.make_mmvt_integrator(syn, "")
     s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=64)
+    assert integ.getDecisionMode() == "local"
+    syn, positions = _shell_workload(512, 3000, H.SEED_BASE + 62)      # 6 144 streaming blocks (> 30 x SMs): HBM-bound batch
+    integ = H.make_mmvt_integrator(syn, "")
+    s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=512)
     assert integ.getDecisionMode() == "handoff"
     syn, positions = _shell_workload(1, 3000, H.SEED_BASE + 62)
     integ = H.make_mmvt_integrator(syn, "")
@@ -145,7 +149,8 @@ KNOB_SETS = [
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_TUNE": "3"},                                                # normals before griddepcontrol.wait
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PACKED": "0"},                                              # aligned layout for one-warp groups
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PDL": "0"},
-    {"SEEKR2_B200_DECIDE": "h", "SEEKR2_B200_TUNE": "4"},                                                # hand-off kernel, optimistic stores
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_REGS": "72"},                                         # the throughput-regime instantiation
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_REGS": "72", "SEEKR2_B200_LOCAL_THREADS": "128", "SEEKR2_B200_LOCAL_RESIDENT": "40"},
 ]
 
 
@@ -153,13 +158,13 @@ KNOB_SETS = [
                                                          ("mmvt", False, "reference", True), ("elber", False, "cuda", False)])
 def test_kernel_knobs_do_not_change_a_bit(cuda_device, monkeypatch, kind, middle, variant, restore):
     """The LOCAL kernel's launch shape (streaming threads per block, tiles per block), the packed / aligned slot layout, early
-    normals, programmatic dependent launch and the hand-off kernel's optimistic stores are tuning knobs: every setting must
+    normals, programmatic dependent launch and the register budget of the LOCAL instantiation are tuning knobs: every setting must
     give the bits of the default hand-off kernel (which the other modules pin to the oracle) -- atoms, records, statistics,
     clock -- on 4 anchors x 3 000 atoms over 400 steps with bounces, under 8-step graph replay."""
     A, n = 4, 3000
 
     def run(env):
-        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL"):
+        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL", "SEEKR2_B200_LOCAL_REGS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -10,7 +10,7 @@ import seekr2_openmm_plugin_b200 as s2
 from seekr2_openmm_plugin_b200 import synthetic as H
 
 NATOMS = int(sys.argv[1]) if len(sys.argv) > 1 else bench.N_ATOMS
-STEPS, G = 4096, bench.STEPS_PER_GRAPH
+STEPS, G = int(os.environ.get("SWEEP_STEPS", "4096")), bench.STEPS_PER_GRAPH
 
 
 def us_per_step(A, kind, mode):
@@ -36,18 +36,23 @@ def us_per_step(A, kind, mode):
             e1.record(ctx.stream)
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / STEPS)
-    assert integ.getDecisionMode() == mode
-    return best
+    assert mode == "auto" or integ.getDecisionMode() == mode
+    return best, integ.getDecisionMode()
 
 
 out = {"atoms": NATOMS, "steps": STEPS, "steps_per_graph": G, "rows": []}
-for A in [int(a) for a in os.environ.get("SWEEP_ANCHORS", "1,2,3,4,6,8,12,16,32").split(",")]:
+for A in [int(a) for a in os.environ.get("SWEEP_ANCHORS", "1,2,4,6,8,12,16,24,32,48,64,96,128").split(",")]:
     row = {"anchors": A}
     for kind in ("mmvt", "langevin"):
-        for mode in ("local", "handoff"):
-            row[f"{kind}_{mode}_us"] = round(us_per_step(A, kind, mode), 3)
-    row["mmvt_over_plain_local"] = round(row["mmvt_local_us"] / min(row["langevin_local_us"], row["langevin_handoff_us"]), 3)
-    row["mmvt_over_plain_handoff"] = round(row["mmvt_handoff_us"] / min(row["langevin_local_us"], row["langevin_handoff_us"]), 3)
+        for mode in ("auto", "local", "handoff"):
+            t, chosen = us_per_step(A, kind, mode)
+            row[f"{kind}_{mode}_us"] = round(t, 3)
+            if mode == "auto" and kind == "mmvt":
+                row["auto_mode"] = chosen
+    plain = min(row["langevin_auto_us"], row["langevin_local_us"], row["langevin_handoff_us"])      # the fastest plain Langevin step, whatever launch shape
+    row["mmvt_over_plain_auto"] = round(row["mmvt_auto_us"] / plain, 3)
+    row["mmvt_over_plain_local"] = round(row["mmvt_local_us"] / plain, 3)
+    row["mmvt_over_plain_handoff"] = round(row["mmvt_handoff_us"] / plain, 3)
     out["rows"].append(row)
     print(json.dumps(row), file=sys.stderr, flush=True)
 print(json.dumps(out))

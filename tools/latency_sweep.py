@@ -14,7 +14,7 @@ import seekr2_openmm_plugin_b200 as s2
 from seekr2_openmm_plugin_b200 import synthetic as H
 
 STEPS, G = int(os.environ.get("SWEEP_STEPS", "4096")), bench.STEPS_PER_GRAPH
-KNOBS = ("SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_PDL")
+KNOBS = ("SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_LOCAL_REGS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_PDL")
 _cache = {}
 
 
@@ -77,9 +77,11 @@ def us_per_step(system, A, kind, mode, knobs):
 
 full = os.environ.get("SWEEP", "quick") == "full"
 tunes = [int(t) for t in os.environ.get("SWEEP_TUNES", "0").split(",")]
-variants = [("local", {"SEEKR2_B200_LOCAL_THREADS": T, "SEEKR2_B200_TUNE": t}) for T in ((64, 128, 192, 256) if full else (128, 256)) for t in tunes]
+extra = [dict(kv.split("=") for kv in v.split("+") if kv) for v in os.environ.get("SWEEP_EXTRA", "").split(",")]   # e.g. SEEKR2_B200_SEGMENTED=0,SEEKR2_B200_CHAIN=0
+threads = [int(t) for t in os.environ.get("SWEEP_THREADS", "64,128,192,256" if full else "128,256").split(",")]
+variants = [("local", {"SEEKR2_B200_LOCAL_THREADS": T, "SEEKR2_B200_TUNE": t, **x}) for T in threads for t in tunes for x in extra]
 if os.environ.get("SWEEP_HANDOFF", "1") == "1":
-    variants += [("handoff", {"SEEKR2_B200_TUNE": t}) for t in (0, 4)]
+    variants += [("handoff", {"SEEKR2_B200_TUNE": 0})]
 if full:
     variants += [("local", {"SEEKR2_B200_LOCAL_THREADS": 128, "SEEKR2_B200_PACKED": 0})]
 anchors = [int(a) for a in os.environ.get("SWEEP_ANCHORS", "1,2,4,8,16,32").split(",")]
@@ -91,8 +93,6 @@ for system, kinds, alist in (("tryp", ("mmvt", "langevin"), anchors), ("hg", ("m
         for mode, knobs in variants:
             row = {"system": system, "anchors": A, "mode": mode, **{k.replace("SEEKR2_B200_", "").lower(): v for k, v in knobs.items()}}
             for kind in kinds:
-                if kind != "mmvt" and knobs.get("SEEKR2_B200_TUNE") == 4:   # the optimistic-store bit only touches the MMVT path
-                    continue
                 row[f"{kind}_us"], b = us_per_step(system, A, kind, mode, knobs)
                 if kind == "mmvt":
                     row["bounce_steps"] = b
