@@ -72,10 +72,20 @@ for middle in (False, True):
     tag = "MIDDLE" if middle else "LANGEVIN"
     if not middle:
         report("kick_kernel (Part1; pool)", timeit(lambda: L.check(L.lib.seekr2_b200_kick(integ._handle, C.byref(bufs), 0, ctx.stream_ptr)), ctx), 136)
-        report("decide_kernel + finish_kernel (Part2 + CV + bounce)", timeit(lambda: L.check(L.lib.seekr2_b200_finish(integ._handle, C.byref(bufs), ctx.stream_ptr)), ctx), 160)
+        report("finish_kernel, one launch: decide blocks + Part2 + bounce", timeit(lambda: L.check(L.lib.seekr2_b200_finish(integ._handle, C.byref(bufs), ctx.stream_ptr)), ctx), 160)
     else:
         report("middle_part1_kernel (force kick)", timeit(lambda: L.check(L.lib.seekr2_b200_kick(integ._handle, C.byref(bufs), 0, ctx.stream_ptr)), ctx), 88)
         report("middle_part2_kernel (O step, posDelta, oldDelta, oldVelm; pool)", timeit(lambda: L.check(L.lib.seekr2_b200_middle_drift(integ._handle, C.byref(bufs), 0, ctx.stream_ptr)), ctx), 176)
-        report("decide_kernel + middle_finish_kernel (Part3 + CV + bounce)", timeit(lambda: L.check(L.lib.seekr2_b200_finish(integ._handle, C.byref(bufs), ctx.stream_ptr)), ctx), 192)
+        report("middle_finish_kernel, one launch: decide blocks + Part3 + bounce", timeit(lambda: L.check(L.lib.seekr2_b200_finish(integ._handle, C.byref(bufs), ctx.stream_ptr)), ctx), 192)
+    if not middle:
+        # the two small launches the OpenMM adapter adds around a fused step: slab re-gather and (on crossing steps) the ring drain
+        us = timeit(lambda: L.check(L.lib.seekr2_b200_resync(integ._handle, C.byref(bufs), ctx.stream_ptr)), ctx)
+        print(f"{'resync_kernel (slab re-gather + step index, 128 anchors x 64 slots)':58s} {us:8.2f} us", flush=True)
+        def drain():
+            L.check(L.lib.seekr2_b200_drain_begin(integ._handle, 4096, ctx.stream_ptr))
+            n = C.c_int64(0)
+            L.check(L.lib.seekr2_b200_drain_end(integ._handle, (L.Record * 4096)(), 4096, C.byref(n), None))
+        us = timeit(drain, ctx, reps=20)
+        print(f"{'ring_pack_kernel + event wait (blocking drain, nothing to fetch)':58s} {us:8.2f} us", flush=True)
     del ctx, integ
 json.dump([dict(kernel=r[0], us=r[1], bytes_per_atom=r[2], gbs=r[3], frac=r[4]) for r in rows], open(os.path.join(ROOT, "gpurun_out", "kernel_bench.json"), "w"), indent=1)
