@@ -52,6 +52,9 @@ protected:
     std::vector<int32_t> slotIndex;  /* current buffer index of every boundary-group atom (cu.getAtomIndex()) */
     void followAtomOrder();
     bool deviceTime(long long stepsIssued, double stepSize, double& time);
+    void noteClock(bool valid);
+    double clockTime = 0.0;          /* the anchor clock that came with the latest collected drain ... */
+    long long clockStep = 0;         /* ... and the step count it belongs to */
     int64_t collectPending(bool block);           /* records handed to writeRecords(); -1 = not ready */
     void flushDrain();
     void writeRecords(int64_t n);

@@ -184,7 +184,7 @@ void B200StepKernelBase::drainTo(const std::string& file, int kind, const std::v
     records.resize(4096);
     int64_t n = 0;
     check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
-    collected = true; clockValid = true;
+    noteClock(true);
     writeRecords(n);
 }
 
@@ -199,7 +199,7 @@ int64_t B200StepKernelBase::collectPending(bool block) {
     int64_t n = 0, waiting = 0;
     check(seekr2_b200_drain_end(handle, records.data(), (int64_t) records.size(), &n, &waiting));
     drainPending = false;
-    collected = true; clockValid = pendingClockValid;
+    noteClock(pendingClockValid);
     writeRecords(n);
     return n;
 }
@@ -211,7 +211,7 @@ void B200StepKernelBase::flushDrain() {
         records.resize(4096);
         int64_t n = 0;
         check(seekr2_b200_drain(handle, records.data(), (int64_t) records.size(), &n, (void*) cu.getCurrentStream()));
-        collected = true; clockValid = true;
+        noteClock(true);
         writeRecords(n);
         total += n;
         if (n < (int64_t) 4096) break;
@@ -227,10 +227,18 @@ void B200StepKernelBase::flushDrain() {
    false when no usable clock has been collected. */
 bool B200StepKernelBase::deviceTime(long long stepsIssued, double stepSize, double& time) {
     if (!collected || !clockValid) return false;
-    int64_t at = 0;
-    check(seekr2_b200_drain_clock(handle, 0, &time, &at));
-    for (long long k = at; k < stepsIssued; k++) time += stepSize;
+    time = clockTime;
+    for (long long k = clockStep; k < stepsIssued; k++) time += stepSize;
     return true;
+}
+
+/* a drain has just been collected: keep its clock (the staging area belongs to the next drain from now on) */
+void B200StepKernelBase::noteClock(bool valid) {
+    collected = true;
+    clockValid = valid;
+    int64_t at = 0;
+    check(seekr2_b200_drain_clock(handle, 0, &clockTime, &at));
+    clockStep = at;
 }
 
 /* CudaSeekr2Kernels.cpp:313-345: rewritten whenever crossings have been logged */
