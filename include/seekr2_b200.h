@@ -87,7 +87,15 @@ enum {
        HANDOFF for batched, bandwidth-bound launches.                                                 */
     SEEKR2_B200_FLAG_DECIDE_LOCAL = 2,       /* every block evaluates the boundaries itself (needs
                                                 save_state_slots == 0 and <= 256 padded group slots)  */
-    SEEKR2_B200_FLAG_DECIDE_HANDOFF = 4      /* one decide block per anchor publishes the decision    */
+    SEEKR2_B200_FLAG_DECIDE_HANDOFF = 4,     /* one decide block per anchor publishes the decision    */
+    /* Boundary value in SINGLE precision, the way OpenMM's CUDA platform evaluates a CustomCentroidBondForce in single
+       and mixed precision (the reference reads that value, CudaSeekr2Kernels.cpp:248): float weights, float group
+       centres accumulated sequentially in group order, float distance = sqrtf(dx*dx + dy*dy + dz*dz), float
+       distance*distance - radius*radius, float k * u.  OpenMM itself is absent here, so this restates its evaluation
+       (tools/cv_float_contract.py) rather than reproducing it bit for bit; the default (0) is the double / fixed-point
+       contract of DESIGN.md section 3, which differs from this on ~1e-5 of the steps of a constantly bouncing run.
+       SPHERE_PAIR / SPHERE_FIXED / PLANE boundaries, SINGLE or MIXED precision; the fused step runs the hand-off kernel. */
+    SEEKR2_B200_FLAG_CV_FLOAT = 8
 };
 
 /* integrator kind */

@@ -310,7 +310,44 @@ static double boundary_term(const seekr2_b200_boundary* b, const double* cen) {
     return ku >= 0 ? b->bitcode : 0.0;   /* step(x) = 0 if x < 0, 1 otherwise */
 }
 
+/* FLAG_CV_FLOAT: the boundary value the way OpenMM's CUDA platform evaluates it in single / mixed precision -- float weights,
+   float centres summed in group order, sqrtf, float distance^2 - radius^2 (restated: tools/cv_float_contract.py, "sequential") */
+static double group_value_float(const seekr2_oracle* o, const void* posq, int forceGroup) {
+    float cen[3 * SEEKR2_B200_MAX_GROUPS];
+    const real4_s* q = (const real4_s*) posq;
+    for (int g = 0; g < o->numGroups; g++) {
+        float acc[3] = { 0.0f, 0.0f, 0.0f };
+        for (int j = o->groupOffsets[g]; j < o->groupOffsets[g + 1]; j++) {
+            const float w = (float) o->groupWeights[j];
+            const real4_s p = q[o->groupAtoms[j]];
+            acc[0] = acc[0] + w * p.x; acc[1] = acc[1] + w * p.y; acc[2] = acc[2] + w * p.z;     /* -ffp-contract=off: no fma */
+        }
+        for (int c = 0; c < 3; c++) cen[3 * g + c] = acc[c];
+    }
+    double value = 0.0;
+    for (int i = 0; i < o->numBoundaries; i++) {
+        const seekr2_b200_boundary* b = &o->boundaries[i];
+        if (b->force_group != forceGroup) continue;
+        const float* ca = cen + 3 * b->groups[0];
+        float u;
+        if (b->type == SEEKR2_B200_CV_PLANE) {
+            u = ca[b->axis] - (float) b->threshold;
+        } else {
+            float d[3];
+            for (int c = 0; c < 3; c++) d[c] = ca[c] - (b->type == SEEKR2_B200_CV_SPHERE_PAIR ? cen[3 * b->groups[1] + c] : (float) b->center[c]);
+            const float r2 = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+            const float dist = sqrtf(r2);
+            const float r = (float) b->threshold;
+            u = dist * dist - r * r;
+        }
+        const float ku = (float) b->k * u;
+        value += b->style == SEEKR2_B200_STYLE_RAW ? (double) ku : (ku >= 0.0f ? b->bitcode : 0.0);
+    }
+    return value;
+}
+
 double seekr2_oracle_group_value(const seekr2_oracle* o, const void* posq, const void* corr, int forceGroup) {
+    if (o->flags & SEEKR2_B200_FLAG_CV_FLOAT) return group_value_float(o, posq, forceGroup);
     double cen[3 * SEEKR2_B200_MAX_GROUPS];
     seekr2_oracle_centroids(o, posq, corr, cen);
     double value = 0.0;

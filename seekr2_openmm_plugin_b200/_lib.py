@@ -26,6 +26,7 @@ VARIANT_CUDA, VARIANT_REFERENCE = 0, 1
 FLAG_RESTORE_CORRECTION = 1
 FLAG_DECIDE_LOCAL = 2
 FLAG_DECIDE_HANDOFF = 4
+FLAG_CV_FLOAT = 8
 KIND_LANGEVIN, KIND_MMVT, KIND_ELBER = 0, 1, 2
 SCHEME_LANGEVIN, SCHEME_MIDDLE = 0, 1
 CV_SPHERE_PAIR, CV_SPHERE_FIXED, CV_PLANE, CV_PAIR_SUM, CV_ANGLE = 0, 1, 2, 3, 4

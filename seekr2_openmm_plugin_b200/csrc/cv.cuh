@@ -66,6 +66,9 @@ struct EngineDev {
     int local_tiles;             // ceil(num_atoms / local_stream_threads): a block walks tiles blockIdx.x, + gridDim.x, ...
     int group_warp_begin[SEEKR2_B200_MAX_GROUPS + 1];   // aligned layout: slot warps [begin[g], begin[g+1]) hold group g
     int has_rare_terms;          // a PAIR_SUM / ANGLE boundary exists (their sums go through shared memory)
+    int group_slot_begin[SEEKR2_B200_MAX_GROUPS];   // first slot of group g and the number of its REAL slots (padding excluded):
+    int group_slot_count[SEEKR2_B200_MAX_GROUPS];   // FLAG_CV_FLOAT sums a group's float terms sequentially in this order
+    unsigned spin_limit;         // polls (64 ns apart) after which a block waiting for an in-launch decision traps (0xffffffff = never)
     int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 2 the hand-off kernel stores optimistically; bit 3 the LOCAL kernel
                                  // releases the next launch right after its own wait instead of after its loads; bit 4 the LOCAL
                                  // kernel's slot warps load with plain L1-bypassing loads instead of L2 evict_last hints
@@ -74,16 +77,62 @@ constexpr int kLayoutAligned = 0, kLayoutPacked = 1;
 constexpr int kTuneHandoffOptimistic = 4, kTuneReleaseFirst = 8, kTunePlainSlotLoads = 16;
 constexpr int kMaxPackedGroups = 4;
 
+constexpr int kCvRound = 256;   // slots handled per round by a decide block (= its thread count)
+
 // shared-memory scratch of the CV phase
 struct CvShared {
     long long acc[SEEKR2_B200_MAX_GROUPS * 3];
+    float facc[SEEKR2_B200_MAX_GROUPS * 3];        // FLAG_CV_FLOAT: float group centres ...
+    float fprod[3][kCvRound];                      // ... and this round's weighted float positions, by slot within the round
     double term[SEEKR2_B200_MAX_BOUNDARIES];
     int force_group[SEEKR2_B200_MAX_BOUNDARIES];
     int bounce;
 };
 
 __device__ __forceinline__ void cv_clear(CvShared& sh, int num_groups) {
-    if (threadIdx.x < num_groups * 3) sh.acc[threadIdx.x] = 0;
+    if (threadIdx.x < num_groups * 3) { sh.acc[threadIdx.x] = 0; sh.facc[threadIdx.x] = 0.0f; }
+}
+
+// ---- FLAG_CV_FLOAT: the boundary value in single precision, restating OpenMM's CUDA CustomCentroidBondForce evaluation
+// (oracle: group_value_float) -- float weights, float centres summed SEQUENTIALLY in group order, sqrtf, float d^2 - r^2.
+// One round = the kCvRound slots [r0, r0 + kCvRound) held one per thread: every thread deposits its weighted position,
+// the block synchronises, thread g adds the real slots of group g that fall into the round, in slot order.
+__device__ __forceinline__ void cvf_round(CvShared& sh, const EngineDev& e, int r0, bool valid, double w, float x, float y, float z) {
+    const float wf = (float) w;
+    sh.fprod[0][threadIdx.x] = valid ? __fmul_rn(wf, x) : 0.0f;
+    sh.fprod[1][threadIdx.x] = valid ? __fmul_rn(wf, y) : 0.0f;
+    sh.fprod[2][threadIdx.x] = valid ? __fmul_rn(wf, z) : 0.0f;
+    __syncthreads();
+    const int g = threadIdx.x;
+    if (g < e.num_groups) {
+        const int lo = max(e.group_slot_begin[g], r0), hi = min(e.group_slot_begin[g] + e.group_slot_count[g], r0 + kCvRound);
+        float a0 = sh.facc[g * 3], a1 = sh.facc[g * 3 + 1], a2 = sh.facc[g * 3 + 2];
+        for (int s = lo; s < hi; s++) {
+            a0 = __fadd_rn(a0, sh.fprod[0][s - r0]); a1 = __fadd_rn(a1, sh.fprod[1][s - r0]); a2 = __fadd_rn(a2, sh.fprod[2][s - r0]);
+        }
+        sh.facc[g * 3] = a0; sh.facc[g * 3 + 1] = a1; sh.facc[g * 3 + 2] = a2;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ double cvf_term(const CvShared& sh, const Boundary& b) {
+    const float* ca = sh.facc + 3 * b.groups[0];
+    float u;
+    if (b.type == SEEKR2_B200_CV_PLANE) {
+        u = __fsub_rn(ca[b.axis], (float) b.threshold);
+    } else {
+        const bool pair = b.type == SEEKR2_B200_CV_SPHERE_PAIR;
+        const float* cb = sh.facc + 3 * b.groups[1];
+        const float d0 = __fsub_rn(ca[0], pair ? cb[0] : (float) b.center[0]);
+        const float d1 = __fsub_rn(ca[1], pair ? cb[1] : (float) b.center[1]);
+        const float d2 = __fsub_rn(ca[2], pair ? cb[2] : (float) b.center[2]);
+        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+        const float dist = __fsqrt_rn(r2);
+        const float r = (float) b.threshold;
+        u = __fsub_rn(__fmul_rn(dist, dist), __fmul_rn(r, r));
+    }
+    const float ku = __fmul_rn((float) b.k, u);
+    if (b.style == SEEKR2_B200_STYLE_RAW) return (double) ku;
+    return ku >= 0.0f ? b.bitcode : 0.0;
 }
 
 // sum over the 32 lanes of a converged warp, modulo 2^64 (exact whenever the true sum fits in int64): three limbs
@@ -227,7 +276,7 @@ __device__ __forceinline__ double cv_term(const CvShared& sh, const Boundary& b)
 // warp 0: lane b evaluates boundary b of this anchor into shared memory
 __device__ __forceinline__ void cv_terms(CvShared& sh, const EngineDev& e, const Boundary& b, int lane = threadIdx.x) {
     if (lane < e.num_boundaries) {
-        sh.term[lane] = cv_term(sh, b);
+        sh.term[lane] = (e.flags_bits & SEEKR2_B200_FLAG_CV_FLOAT) ? cvf_term(sh, b) : cv_term(sh, b);
         sh.force_group[lane] = b.force_group;
     }
     __syncwarp();

@@ -374,6 +374,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             for (int g = 0; g < used; g++)
                 if (bd.groups[g] < 0 || bd.groups[g] >= cfg->num_groups) return fail(SEEKR2_B200_ERR_INVALID, "boundary %d: bad group index %d", i, bd.groups[g]);
         }
+    if (cfg->flags & SEEKR2_B200_FLAG_CV_FLOAT) {
+        if (cfg->precision == DOUBLE) return fail(SEEKR2_B200_ERR_INVALID, "FLAG_CV_FLOAT is for SINGLE and MIXED precision (OpenMM evaluates in double in double precision)");
+        for (size_t i = 0; i < (size_t) cfg->num_anchors * cfg->num_boundaries; i++)
+            if (cfg->boundaries[i].type > SEEKR2_B200_CV_PLANE) return fail(SEEKR2_B200_ERR_INVALID, "FLAG_CV_FLOAT supports SPHERE_PAIR, SPHERE_FIXED and PLANE boundaries");
+    }
     if (cfg->kind == SEEKR2_B200_KIND_ELBER) {
         // every milestone's force group must carry a Force (CudaSeekr2Kernels.cpp:415-436)
         for (int pass = 0; pass < 2; pass++) {
@@ -417,7 +422,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
     int local_threads = kThreads;
     {
         const long long stream_blocks = (long long) A * ((cfg->num_atoms + kThreads - 1) / kThreads);
-        const bool eligible = snap_slots == 0 && aligned_slots <= kThreads;
+        const bool eligible = snap_slots == 0 && aligned_slots <= kThreads && !(cfg->flags & SEEKR2_B200_FLAG_CV_FLOAT);
         long long limit = (long long) prop.multiProcessorCount * kLocalBlocksPerSm;
         if (const char* lm = getenv("SEEKR2_B200_LOCAL_LIMIT")) limit = atoll(lm);                                   // tuning knob
         local = eligible && stream_blocks <= limit;
@@ -467,6 +472,11 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             for (size_t j = first; j < slot_atom.size(); j++) slot_group[j] |= kGroupSingleWarp;
     }
     const int num_slots = (int) slot_atom.size();
+    for (int g = 0; g < SEEKR2_B200_MAX_GROUPS; g++) { d.group_slot_begin[g] = 0; d.group_slot_count[g] = 0; }
+    for (int s = 0, g = -1; s < num_slots; s++) {
+        const int gs = slot_group[s] & (kGroupSingleWarp - 1);
+        if (gs != g) { g = gs; d.group_slot_begin[g] = s; d.group_slot_count[g] = cfg->group_offsets[g + 1] - cfg->group_offsets[g]; }
+    }
     d.slot_layout = (packed || num_slots == 0) ? kLayoutPacked : kLayoutAligned;
     d.slot_threads = d.slot_layout == kLayoutPacked ? 32 : num_slots;
     {
@@ -477,6 +487,8 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         d.local_tiles = (cfg->num_atoms + T - 1) / T;
     }
     d.tune = 0;
+    d.spin_limit = 40000000u;                      // ~2.5 s of 64 ns polls
+    if (const char* sl = getenv("SEEKR2_B200_SPIN_LIMIT")) { const long long v = atoll(sl); d.spin_limit = v <= 0 ? 0xffffffffu : (unsigned) (v > 0xfffffffeLL ? 0xfffffffeLL : v); }
     if (const char* tn = getenv("SEEKR2_B200_TUNE")) d.tune = atoi(tn);                                             // tuning knob
     d.num_atoms = cfg->num_atoms; d.padded_num_atoms = cfg->padded_num_atoms; d.num_anchors = A;
     d.num_slots = num_slots; d.num_groups = cfg->num_groups; d.num_boundaries = cfg->num_boundaries;

@@ -84,6 +84,12 @@ class _B200LangevinBase:
     def setRestoreCorrection(self, on: bool) -> None:
         self.flags = (self.flags | L.FLAG_RESTORE_CORRECTION) if on else (self.flags & ~L.FLAG_RESTORE_CORRECTION)
 
+    def setBoundaryValueInFloat(self, on: bool) -> None:
+        """Evaluate the boundary value in single precision, restating OpenMM's CUDA ``CustomCentroidBondForce`` evaluation
+        (``SEEKR2_B200_FLAG_CV_FLOAT``), instead of the default double / fixed-point contract.  Takes effect when the
+        Context is created."""
+        self.flags = (self.flags | L.FLAG_CV_FLOAT) if on else (self.flags & ~L.FLAG_CV_FLOAT)
+
     def setDecisionMode(self, mode: str) -> None:
         """How the fused step hands the crossing decision to the storing threads: "auto" (by launch size), "local"
         (every block evaluates the boundaries; latency-bound launches) or "handoff" (one decide block per anchor).

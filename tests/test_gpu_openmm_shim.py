@@ -338,13 +338,13 @@ def test_elber_missing_force_group_message(cuda_device, tmp_path):
 
 @pytest.mark.parametrize("mode", ["default", "blocking_drain"])
 def test_elber_many_clock_resets(cuda_device, tmp_path, mode):
-    """A run that sits on its source milestone (high friction, destinations far away): the source is crossed again and again,
+    """A run that sits on its source milestone (tethered atoms, destinations far away): the source is crossed again and again,
     each crossing resets the clock on the device (:545), the adapter learns of it through the reset counter in mapped
     memory and queues drain after drain -- a collected drain is often followed by the next one within the same execute().
     Context time and the final buffers must still equal the reference's, which reads the values back every step."""
     host, guest = list(range(0, 11)), list(range(11, 20))
-    syn = H.pair_sphere_system(300, host, guest, 0.30, 0.50, H.SEED_BASE + 5, tether_k=0.0)
-    syn.friction = 50.0
+    syn = H.pair_sphere_system(300, host, guest, 0.30, 0.50, H.SEED_BASE + 5, tether_k=500.0)     # tethered: it keeps coming back
+    syn.friction = 5.0
     syn.system._forces = [f for f in syn.system._forces if not isinstance(f, s2.CustomCentroidBondForce)]
     for group, radius in ((1, 0.40), (2, 0.30), (3, 0.50)):
         f = s2.CustomCentroidBondForce(2, "bitcode*step(k*(distance(g1,g2)^2-radius^2))")
@@ -362,4 +362,4 @@ def test_elber_many_clock_resets(cuda_device, tmp_path, mode):
     assert_same_outputs(out, "mixed", 300, min_lines=2)
     (rd, _), (bd, _) = out["ref"], out["b200"]
     _, t_ref, _ = read_dump(rd / "dump.bin", "mixed", 300)
-    assert 0.0 < t_ref < 0.9 * steps * syn.dt, t_ref          # the clock was reset well after the start of the run
+    assert 0.0 < t_ref < 0.5 * steps * syn.dt, t_ref          # the clock was last reset in the second half of the run
