@@ -51,6 +51,10 @@ void B200StepKernelBase::create(const System& system, seekr2_b200_config& cfg, i
     cfg.abi_version = SEEKR2_B200_ABI_VERSION;
     cfg.precision = cu.getUseDoublePrecision() ? SEEKR2_B200_DOUBLE : cu.getUseMixedPrecision() ? SEEKR2_B200_MIXED : SEEKR2_B200_SINGLE;
     cfg.variant = SEEKR2_B200_VARIANT_CUDA;
+    /* OpenMM evaluates the boundary expressions in float in single / mixed precision; the engine's default is an
+       order-independent double / fixed-point evaluation (1-2.5 decisions in 10^5 steps of a constantly bouncing run differ,
+       DESIGN.md section 3).  SEEKR2_B200_CV_FLOAT=1 selects the engine's float restatement of OpenMM's evaluation instead. */
+    if (const char* f = getenv("SEEKR2_B200_CV_FLOAT")) if (f[0] == '1' && !cu.getUseDoublePrecision()) cfg.flags |= SEEKR2_B200_FLAG_CV_FLOAT;
     cfg.device = cu.getDeviceIndex();
     cfg.num_anchors = 1;
     cfg.num_atoms = cu.getNumAtoms();
