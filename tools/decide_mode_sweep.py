@@ -44,15 +44,15 @@ out = {"atoms": NATOMS, "steps": STEPS, "steps_per_graph": G, "rows": []}
 for A in [int(a) for a in os.environ.get("SWEEP_ANCHORS", "1,2,4,6,8,12,16,24,32,48,64,96,128").split(",")]:
     row = {"anchors": A}
     for kind in ("mmvt", "langevin"):
-        for mode in ("auto", "local", "handoff"):
+        for mode in os.environ.get("SWEEP_MODES", "auto,local,handoff").split(","):
             t, chosen = us_per_step(A, kind, mode)
             row[f"{kind}_{mode}_us"] = round(t, 3)
             if mode == "auto" and kind == "mmvt":
                 row["auto_mode"] = chosen
-    plain = min(row["langevin_auto_us"], row["langevin_local_us"], row["langevin_handoff_us"])      # the fastest plain Langevin step, whatever launch shape
-    row["mmvt_over_plain_auto"] = round(row["mmvt_auto_us"] / plain, 3)
-    row["mmvt_over_plain_local"] = round(row["mmvt_local_us"] / plain, 3)
-    row["mmvt_over_plain_handoff"] = round(row["mmvt_handoff_us"] / plain, 3)
+    modes = os.environ.get("SWEEP_MODES", "auto,local,handoff").split(",")
+    plain = min(row[f"langevin_{m}_us"] for m in modes)      # the fastest plain Langevin step, whatever launch shape
+    for m in modes:
+        row[f"mmvt_over_plain_{m}"] = round(row[f"mmvt_{m}_us"] / plain, 3)
     out["rows"].append(row)
     print(json.dumps(row), file=sys.stderr, flush=True)
 print(json.dumps(out))
