@@ -74,6 +74,29 @@ def test_elber_missing_force_group_is_rejected():
     assert b"no force groups used to detect Elber boundary crossings" in L.lib.seekr2_b200_last_error()
 
 
+def test_float_boundary_flag_is_validated_before_cuda():
+    """FLAG_CV_FLOAT restates OpenMM's single-precision evaluation: meaningless in double precision, and defined for spheres and
+    planes only -- rejected by create() before any device work."""
+    syn = H.toy_system()
+    integ = H.make_mmvt_integrator(syn, "")
+    integ.setBoundaryValueInFloat(True)
+    h = C.c_void_p()
+    cfg = integ.makeConfig(syn.system, L.DOUBLE)
+    assert L.lib.seekr2_b200_create(C.byref(cfg), C.byref(h)) == L.ERR_INVALID
+    assert b"FLAG_CV_FLOAT" in L.lib.seekr2_b200_last_error()
+
+
+def test_strict_boundary_parameters_in_the_harness():
+    """A name in the boundary expression that is not a per-bond parameter is an error, not a silent default."""
+    syn = H.toy_system()
+    f = syn.boundary_force
+    f.param_names[f.param_names.index("radius")] = "rad"
+    integ = H.make_mmvt_integrator(syn, "")
+    with pytest.raises(L.Seekr2Error) as err:
+        integ.makeConfig(syn.system, L.MIXED)
+    assert "not a per-bond parameter" in str(err.value)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
