@@ -46,7 +46,7 @@ int fail(int code, const char* fmt, ...) {
 // OpenMM SimTKOpenMMRealType.h: BOLTZ = RGAS/KILO with RGAS = BOLTZMANN*AVOGADRO (CODATA 2018);
 // the constant multiplied by the temperature at CudaSeekr2Kernels.cpp:191.
 // auto mode (measured on 23 036-atom anchors, profiles/r02_local_regs_sweep.json; streaming blocks = anchors x ceil(atoms / 256)):
-//   up to  4 x SMs blocks (<= 6 anchors)   LOCAL decision, 96 registers, 256 streaming threads per block
+//   up to  4 x SMs blocks (<= 6 anchors)   LOCAL decision, 96 registers, 128 streaming threads per block
 //   up to 12 x SMs blocks (<= 19 anchors)  LOCAL decision, 72 registers, 128 streaming threads per block
 //   up to 30 x SMs blocks (<= 49 anchors)  LOCAL decision, 72 registers, 256 streaming threads per block
 //   beyond                                 decide-block hand-off (HBM-bound: 48 registers, 1280 resident threads per SM)
@@ -439,7 +439,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         // register budget and block size of the LOCAL kernel: latency regime (one round of tiles) vs throughput regime
         const bool latency = stream_blocks <= (long long) prop.multiProcessorCount * kLocalLatencyBlocksPerSm;
         h->local_regs = latency ? kLocalRegsLatency : kLocalRegsThroughput;
-        if (!latency && stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;
+        if (stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;   // also the latency regime: host-guest size 2.51 vs 2.70 us (plain 1.48 vs 1.69), one trypsin anchor 2.27 vs 2.27 (plain 1.73 vs 1.85)
         if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : kLocalRegsLatency;   // A/B knob
         if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
     }
