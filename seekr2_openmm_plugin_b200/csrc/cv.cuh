@@ -64,6 +64,8 @@ struct EngineDev {
     int slot_threads;            // slot threads per block: 32 (packed, or no slots at all) or num_slots (aligned, a multiple of 32)
     int local_stream_threads;    // streaming threads per block (a multiple of 32); one atom per thread and tile
     int local_tiles;             // ceil(num_atoms / local_stream_threads): a block walks tiles blockIdx.x, + gridDim.x, ...
+    int local_undo_tiles;        // MMVT: tiles per block whose pre-step position and bounce velocity are logged in shared memory, so that
+                                 // the streaming warps store optimistically and never wait for the decision (0 = off; sized at the first launch)
     int group_warp_begin[SEEKR2_B200_MAX_GROUPS + 1];   // aligned layout: slot warps [begin[g], begin[g+1]) hold group g
     int has_rare_terms;          // a PAIR_SUM / ANGLE boundary exists (their sums go through shared memory)
     int group_slot_begin[SEEKR2_B200_MAX_GROUPS];   // first slot of group g and the number of its REAL slots (padding excluded):
@@ -71,10 +73,11 @@ struct EngineDev {
     unsigned spin_limit;         // polls (64 ns apart) after which a block waiting for an in-launch decision traps (0xffffffff = never)
     int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 3 the LOCAL kernel
                                  // releases the next launch right after its own wait instead of after its loads; bit 4 the LOCAL
-                                 // kernel's slot warps load with plain L1-bypassing loads instead of L2 evict_last hints
+                                 // kernel's slot warps load with plain L1-bypassing loads instead of L2 evict_last hints; bit 5 the
+                                 // LOCAL kernel's slot warp joins the undo barrier on bounce steps only
 };
 constexpr int kLayoutAligned = 0, kLayoutPacked = 1;
-constexpr int kTuneReleaseFirst = 8, kTunePlainSlotLoads = 16;
+constexpr int kTuneReleaseFirst = 8, kTunePlainSlotLoads = 16, kTuneLazyUndoSync = 32;
 constexpr int kMaxPackedGroups = 4;
 
 constexpr int kCvRound = 256;   // slots handled per round by a decide block (= its thread count)

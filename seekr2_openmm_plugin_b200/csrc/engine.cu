@@ -8,6 +8,7 @@
 // no energy readback, no host branch for the bounce, no file I/O inside the step.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -79,6 +80,7 @@ struct seekr2_b200_engine {
     bool use_pdl = true;            // fused step kernels are launched with programmatic stream serialization (SEEKR2_B200_PDL=0: off)
     bool local_decide = false;      // fused step uses fused_local_kernel (every block decides) instead of the decide-block hand-off
     int local_regs = 96;            // LOCAL mode: register budget of the instantiation that runs (kLocalRegsLatency / kLocalRegsThroughput)
+    size_t local_dyn_smem = 0;      // LOCAL mode, MMVT: bytes of the undo log per block (dev.local_undo_tiles tiles)
     int local_grid_x = 0;           // LOCAL mode: blocks per anchor (0 = not sized yet; sized at the first launch from the occupancy of the
                                     // instantiation that runs, so that the whole grid is resident at once)
     int sm_count = 0;
@@ -218,11 +220,43 @@ template <int P, int KIND, int SCHEME, int REGS> int launch_local(seekr2_b200_en
             if (gx < 1) gx = 1;
             if (gx > h->dev.local_tiles) gx = h->dev.local_tiles;
             h->local_grid_x = (int) gx;
+            // MMVT: the undo log in shared memory (kernels.cuh) -- one entry per streaming thread and tile a block walks, as many
+            // tiles as fit without taking a resident block away from the SM
+            h->dev.local_undo_tiles = 0;
+            h->local_dyn_smem = 0;
+            bool want_undo = KIND == SEEKR2_B200_KIND_MMVT && !(h->cfg.flags & SEEKR2_B200_FLAG_RESTORE_CORRECTION);
+            if (const char* u = getenv("SEEKR2_B200_LOCAL_UNDO")) want_undo = want_undo && atoi(u) != 0;             // A/B knob
+            if (want_undo) {
+                const size_t per_tile = (size_t) T * (sizeof(typename Prec<P>::real4) + sizeof(typename Prec<P>::mixed4));
+                const int need_per_sm = (int) ((gx * h->cfg.num_anchors + h->sm_count - 1) / h->sm_count);
+                // measured (profiles/r02_local_undo_sweep.json): a block that walks ONE tile gains nothing from the log (the slot chain is
+                // the step: 2.34 vs 2.40 us at one anchor -- it keeps that tile in registers and waits); two logged tiles are enough
+                // for blocks of up to four tiles, one for longer walks (a round of tiles takes as long as the slot chain, and a
+                // large log takes the L1 away from the streaming loads: 32 anchors 14.8 us with one logged tile, 16.6 with all)
+                const int tpb = (int) ((h->dev.local_tiles + gx - 1) / gx);
+                int U = tpb <= 1 ? 0 : tpb <= 4 ? std::min(tpb, 2) : 1;
+                if (const char* u = getenv("SEEKR2_B200_LOCAL_UNDO_TILES")) U = std::min(tpb, atoi(u));              // A/B knob
+                cudaFuncAttributes fa;
+                CUDA_TRY(cudaFuncGetAttributes(&fa, fused_local_kernel<P, KIND, SCHEME, REGS>));
+                int optin = 0;
+                CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+                const size_t max_dyn = (size_t) optin > fa.sharedSizeBytes ? (size_t) optin - fa.sharedSizeBytes : 0;
+                while (U > 0 && (size_t) U * per_tile > max_dyn) U--;
+                if (U > 0) CUDA_TRY(cudaFuncSetAttribute(fused_local_kernel<P, KIND, SCHEME, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) U * per_tile)));
+                for (; U > 0; U--) {
+                    int occ = 0;
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_local_kernel<P, KIND, SCHEME, REGS>, (int) threads, (size_t) U * per_tile));
+                    if (occ >= need_per_sm) break;
+                }
+                h->dev.local_undo_tiles = U;
+                h->local_dyn_smem = (size_t) U * per_tile;
+            }
         }
         // programmatic dependent launch: the next step's blocks may start their (static) prologue under this launch's body
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned) h->local_grid_x, (unsigned) h->cfg.num_anchors, 1);
         lc.blockDim = dim3(threads, 1, 1);
+        lc.dynamicSmemBytes = h->local_dyn_smem;
         lc.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -151,6 +151,14 @@ KNOB_SETS = [
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PDL": "0"},
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_REGS": "72"},                                         # the throughput-regime instantiation
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_REGS": "72", "SEEKR2_B200_LOCAL_THREADS": "128", "SEEKR2_B200_LOCAL_RESIDENT": "40"},
+    # the undo log in shared memory (MMVT): off (every block waits for the decision after its first tile); one or two logged tiles
+    # of the many a block walks (log, then one tile from registers behind the decision barrier, then predicated stores); the slot
+    # warp joining the undo barrier on bounce steps only
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_UNDO": "0"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": "1"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "96", "SEEKR2_B200_LOCAL_RESIDENT": "20", "SEEKR2_B200_LOCAL_UNDO_TILES": "2", "SEEKR2_B200_TUNE": "32"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_UNDO_TILES": "1", "SEEKR2_B200_TUNE": "32"},          # the only tile of every block logged
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": "99"},   # 47 tiles, all logged (144 KB)
 ]
 
 
@@ -164,7 +172,8 @@ def test_kernel_knobs_do_not_change_a_bit(cuda_device, monkeypatch, kind, middle
     A, n = 4, 3000
 
     def run(env):
-        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL", "SEEKR2_B200_LOCAL_REGS"):
+        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL", "SEEKR2_B200_LOCAL_REGS",
+                  "SEEKR2_B200_LOCAL_UNDO", "SEEKR2_B200_LOCAL_UNDO_TILES"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
