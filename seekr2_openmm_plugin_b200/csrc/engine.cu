@@ -190,6 +190,8 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
     const bool pdl = h->use_pdl && !h->plain_next;
     if (h->local_decide)
         return h->local_regs == kLocalRegsThroughput ? launch_local<P, KIND, SCHEME, kLocalRegsThroughput>(h, b, ri, s, pdl)
+               : h->local_regs == 56 ? launch_local<P, KIND, SCHEME, 56>(h, b, ri, s, pdl)
+               : h->local_regs == 48 ? launch_local<P, KIND, SCHEME, 48>(h, b, ri, s, pdl)
                                                      : launch_local<P, KIND, SCHEME, kLocalRegsLatency>(h, b, ri, s, pdl);
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
     cudaLaunchConfig_t lc = {};
@@ -474,7 +476,13 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         const bool latency = stream_blocks <= (long long) prop.multiProcessorCount * kLocalLatencyBlocksPerSm;
         h->local_regs = latency ? kLocalRegsLatency : kLocalRegsThroughput;
         if (stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;   // also the latency regime: host-guest size 2.51 vs 2.70 us (plain 1.48 vs 1.69), one trypsin anchor 2.27 vs 2.27 (plain 1.73 vs 1.85)
-        if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : kLocalRegsLatency;   // A/B knob
+        {   // one or two anchors of a large system: 192-thread tiles fill the GPU with one or two blocks per SM -- fewer, evenly spread
+            // blocks, and fewer slot warps asking L2 for the same lines (23 036 atoms: one anchor 1.94 vs 2.07 us, two 2.35 vs 2.61;
+            // profiles/r02_local_threads_sweep.json)
+            const long long b192 = (long long) A * ((cfg->num_atoms + 191) / 192);
+            if (2 * b192 >= prop.multiProcessorCount && b192 <= 2LL * prop.multiProcessorCount) local_threads = 192;
+        }
+        if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : atoi(lr) == 56 ? 56 : atoi(lr) == 48 ? 48 : kLocalRegsLatency;   // A/B knob
         if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
     }
 
@@ -566,6 +574,27 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         const Boundary& bd = cfg->boundaries[i];
         if (bd.force_group == 1 && !(bd.style == SEEKR2_B200_STYLE_STEP && bd.bitcode >= 1.0 && bd.bitcode <= 2147483648.0)) d.mmvt_any_term = 0;
         if (bd.type > SEEKR2_B200_CV_PLANE) d.has_rare_terms = 1;
+    }
+    // the common MMVT anchor -- inner and outer sphere around one pair of groups: the LOCAL kernel's packed slot warp then sums the
+    // difference of the two centroids directly (kernels.cuh)
+    d.pair_fast = 0;
+    if (packed && cfg->num_boundaries > 0 && !(cfg->flags & SEEKR2_B200_FLAG_CV_FLOAT)) {
+        const int ga = cfg->boundaries[0].groups[0], gb = cfg->boundaries[0].groups[1];
+        bool ok = ga != gb, cmp = true;
+        for (size_t i = 0; ok && i < (size_t) A * cfg->num_boundaries; i++) {
+            const Boundary& bd = cfg->boundaries[i];
+            ok = bd.type == SEEKR2_B200_CV_SPHERE_PAIR && ((bd.groups[0] == ga && bd.groups[1] == gb) || (bd.groups[0] == gb && bd.groups[1] == ga));
+            // 2: the term's activity is read off a comparison of the squared distance with the squared radius -- exact when k (d^2 - r^2)
+            // cannot underflow or overflow (d^2 - r^2 is 0 or at least an ulp of r^2 in magnitude) and nothing is NaN
+            const double ak = fabs(bd.k), ar = fabs(bd.threshold);
+            cmp = cmp && bd.style == SEEKR2_B200_STYLE_STEP && ak >= 0x1p-100 && ak <= 0x1p100 && ar >= 0x1p-100 && ar <= 0x1p100;
+        }
+        if (const char* pf = getenv("SEEKR2_B200_PAIR_FAST")) {                                                       // A/B knob
+            if (pf[0] == '0') ok = false;
+            if (pf[0] == '1') cmp = false;
+        }
+        d.pair_fast = ok ? (cmp ? 2 : 1) : 0;
+        d.pair_ga = ga; d.pair_gb = gb;
     }
     CREATE_TRY(cudaMalloc(&h->d_state, sizeof(AnchorState) * A));
     CREATE_TRY(cudaMalloc(&h->d_ring, sizeof(Record) * (size_t) A * d.ring_capacity));

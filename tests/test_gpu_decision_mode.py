@@ -159,6 +159,10 @@ KNOB_SETS = [
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "96", "SEEKR2_B200_LOCAL_RESIDENT": "20", "SEEKR2_B200_LOCAL_UNDO_TILES": "2", "SEEKR2_B200_TUNE": "32"},
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_UNDO_TILES": "1", "SEEKR2_B200_TUNE": "32"},          # the only tile of every block logged
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": "99"},   # 47 tiles, all logged (144 KB)
+    # the one-pair fast path of the packed slot warp (default here: difference of the centroid sums reduced directly, activity read
+    # off a comparison): off, and with the general term evaluation
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PAIR_FAST": "0"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PAIR_FAST": "1", "SEEKR2_B200_LOCAL_THREADS": "160"},
 ]
 
 
@@ -173,7 +177,7 @@ def test_kernel_knobs_do_not_change_a_bit(cuda_device, monkeypatch, kind, middle
 
     def run(env):
         for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_TUNE", "SEEKR2_B200_PACKED", "SEEKR2_B200_PDL", "SEEKR2_B200_LOCAL_REGS",
-                  "SEEKR2_B200_LOCAL_UNDO", "SEEKR2_B200_LOCAL_UNDO_TILES"):
+                  "SEEKR2_B200_LOCAL_UNDO", "SEEKR2_B200_LOCAL_UNDO_TILES", "SEEKR2_B200_PAIR_FAST"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

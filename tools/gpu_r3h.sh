@@ -1,0 +1,7 @@
+mkdir -p gpurun_out/r3h
+timeout 1500 python -m pytest tests/test_gpu_decision_mode.py tests/test_gpu_fuzz.py tests/test_gpu_parity.py tests/test_gpu_bench_config.py tests/test_gpu_scenarios.py tests/test_gpu_known_answers.py -m gpu -x -q > gpurun_out/r3h/tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r3h/tests.log
+export SWEEP_STEPS=4096 SWEEP_MODES=local SWEEP_ANCHORS=1,2,4,8,16
+timeout 600 python tools/decide_mode_sweep.py > gpurun_out/r3h/sweep_fast.json 2> gpurun_out/r3h/sweep_fast.err; echo "sweep rc=$?"; cut -c1-120 gpurun_out/r3h/sweep_fast.err
+SEEKR2_B200_PAIR_FAST=0 timeout 600 python tools/decide_mode_sweep.py > gpurun_out/r3h/sweep_nofast.json 2> gpurun_out/r3h/sweep_nofast.err; echo "sweep nofast rc=$?"; cut -c1-120 gpurun_out/r3h/sweep_nofast.err
+export SEEKR2_B200_LIBRARY=seekr2_openmm_plugin_b200/libseekr2_b200_probe.so PROBE_GRAPH=1 PROBE_STEPS=128
+python tools/handoff_probe.py 1 23036 local 2>&1 | grep -v "^iter\|streaming blocks that" | tail -2 | tee gpurun_out/r3h/probe.txt
