@@ -73,13 +73,10 @@ struct EngineDev {
     int group_slot_begin[SEEKR2_B200_MAX_GROUPS];   // first slot of group g and the number of its REAL slots (padding excluded):
     int group_slot_count[SEEKR2_B200_MAX_GROUPS];   // FLAG_CV_FLOAT sums a group's float terms sequentially in this order
     unsigned spin_limit;         // polls (64 ns apart) after which a block waiting for an in-launch decision traps (0xffffffff = never)
-    int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 3 the LOCAL kernel
-                                 // releases the next launch right after its own wait instead of after its loads; bit 4 the LOCAL
-                                 // kernel's slot warps load with plain L1-bypassing loads instead of L2 evict_last hints; bit 5 the
-                                 // LOCAL kernel's slot warp joins the undo barrier on bounce steps only
+    int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 5 the LOCAL kernel's slot warp joins the undo barrier on bounce steps only
 };
 constexpr int kLayoutAligned = 0, kLayoutPacked = 1;
-constexpr int kTuneReleaseFirst = 8, kTunePlainSlotLoads = 16, kTuneLazyUndoSync = 32;
+constexpr int kTuneLazyUndoSync = 32;
 constexpr int kMaxPackedGroups = 4;
 
 constexpr int kCvRound = 256;   // slots handled per round by a decide block (= its thread count)

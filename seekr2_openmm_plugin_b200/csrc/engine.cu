@@ -189,10 +189,12 @@ template <int P, int KIND, int SCHEME> int launch_fused(seekr2_b200_engine* h, c
     const int bpa = (h->cfg.num_atoms + kThreads - 1) / kThreads;
     const bool pdl = h->use_pdl && !h->plain_next;
     if (h->local_decide)
-        return h->local_regs == kLocalRegsThroughput ? launch_local<P, KIND, SCHEME, kLocalRegsThroughput>(h, b, ri, s, pdl)
-               : h->local_regs == 56 ? launch_local<P, KIND, SCHEME, 56>(h, b, ri, s, pdl)
-               : h->local_regs == 48 ? launch_local<P, KIND, SCHEME, 48>(h, b, ri, s, pdl)
-                                                     : launch_local<P, KIND, SCHEME, kLocalRegsLatency>(h, b, ri, s, pdl);
+    {
+        if constexpr (KIND == SEEKR2_B200_KIND_LANGEVIN)
+            if (h->local_regs == kLocalRegsPlain) return launch_local<P, KIND, SCHEME, kLocalRegsPlain>(h, b, ri, s, pdl);
+        return h->local_regs == kLocalRegsLatency ? launch_local<P, KIND, SCHEME, kLocalRegsLatency>(h, b, ri, s, pdl)
+                                                  : launch_local<P, KIND, SCHEME, kLocalRegsThroughput>(h, b, ri, s, pdl);
+    }
     const unsigned grid = (unsigned) h->cfg.num_anchors * (unsigned) (bpa + 1);   // A decide blocks first, then the streaming blocks
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid, 1, 1);
@@ -474,7 +476,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         h->local_decide = local;
         // register budget and block size of the LOCAL kernel: latency regime (one round of tiles) vs throughput regime
         const bool latency = stream_blocks <= (long long) prop.multiProcessorCount * kLocalLatencyBlocksPerSm;
-        h->local_regs = latency ? kLocalRegsLatency : kLocalRegsThroughput;
+        h->local_regs = latency ? kLocalRegsLatency : cfg->kind == SEEKR2_B200_KIND_LANGEVIN ? kLocalRegsPlain : kLocalRegsThroughput;
         if (stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;   // also the latency regime: host-guest size 2.51 vs 2.70 us (plain 1.48 vs 1.69), one trypsin anchor 2.27 vs 2.27 (plain 1.73 vs 1.85)
         {   // one or two anchors of a large system: 192-thread tiles fill the GPU with one or two blocks per SM -- fewer, evenly spread
             // blocks, and fewer slot warps asking L2 for the same lines (23 036 atoms: one anchor 1.94 vs 2.07 us, two 2.35 vs 2.61;
@@ -482,7 +484,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
             const long long b192 = (long long) A * ((cfg->num_atoms + 191) / 192);
             if (2 * b192 >= prop.multiProcessorCount && b192 <= 2LL * prop.multiProcessorCount) local_threads = 192;
         }
-        if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : atoi(lr) == 56 ? 56 : atoi(lr) == 48 ? 48 : kLocalRegsLatency;   // A/B knob
+        if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : atoi(lr) == kLocalRegsPlain ? kLocalRegsPlain : kLocalRegsLatency;   // A/B knob (48: plain Langevin only)
         if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
     }
 

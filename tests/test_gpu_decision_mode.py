@@ -145,8 +145,7 @@ def test_long_run_local_equals_handoff(cuda_device):
 KNOB_SETS = [
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "128"},
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6"},      # one block per anchor walks every tile
-    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "96", "SEEKR2_B200_LOCAL_RESIDENT": "20", "SEEKR2_B200_TUNE": "24"},
-    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_TUNE": "24"},                                               # dependents released right after the wait, plain slot loads
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "96", "SEEKR2_B200_LOCAL_RESIDENT": "20"},
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PACKED": "0"},                                              # aligned layout for one-warp groups
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PDL": "0"},
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_REGS": "72"},                                         # the throughput-regime instantiation
