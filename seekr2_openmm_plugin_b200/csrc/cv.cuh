@@ -68,7 +68,7 @@ struct EngineDev {
                                  // the streaming warps store optimistically and never wait for the decision (0 = off; sized at the first launch)
     int group_warp_begin[SEEKR2_B200_MAX_GROUPS + 1];   // aligned layout: slot warps [begin[g], begin[g+1]) hold group g
     int has_rare_terms;          // a PAIR_SUM / ANGLE boundary exists (their sums go through shared memory)
-    int pair_fast;               // packed layout and every boundary of every anchor is a SPHERE_PAIR on the same two groups
+    int pair_fast;               // LOCAL mode and every boundary of every anchor is a SPHERE_PAIR on the same two groups
     int pair_ga, pair_gb;        // (pair_ga, pair_gb): the LOCAL kernel reduces the DIFFERENCE of the two centroid sums directly
     int group_slot_begin[SEEKR2_B200_MAX_GROUPS];   // first slot of group g and the number of its REAL slots (padding excluded):
     int group_slot_count[SEEKR2_B200_MAX_GROUPS];   // FLAG_CV_FLOAT sums a group's float terms sequentially in this order

@@ -577,10 +577,10 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         if (bd.force_group == 1 && !(bd.style == SEEKR2_B200_STYLE_STEP && bd.bitcode >= 1.0 && bd.bitcode <= 2147483648.0)) d.mmvt_any_term = 0;
         if (bd.type > SEEKR2_B200_CV_PLANE) d.has_rare_terms = 1;
     }
-    // the common MMVT anchor -- inner and outer sphere around one pair of groups: the LOCAL kernel's packed slot warp then sums the
-    // difference of the two centroids directly (kernels.cuh)
+    // the common MMVT anchor -- inner and outer sphere around one pair of groups: the LOCAL kernel's slot warps then sum the
+    // difference of the two centroids directly (kernels.cuh; both slot layouts)
     d.pair_fast = 0;
-    if (packed && cfg->num_boundaries > 0 && !(cfg->flags & SEEKR2_B200_FLAG_CV_FLOAT)) {
+    if (local && cfg->num_boundaries > 0 && !(cfg->flags & SEEKR2_B200_FLAG_CV_FLOAT)) {
         const int ga = cfg->boundaries[0].groups[0], gb = cfg->boundaries[0].groups[1];
         bool ok = ga != gb, cmp = true;
         for (size_t i = 0; ok && i < (size_t) A * cfg->num_boundaries; i++) {
@@ -839,7 +839,9 @@ int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
     DeviceGuard guard(h->device);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
-    CUDA_TRY(cudaStreamBeginCapture((cudaStream_t) stream, cudaStreamCaptureModeThreadLocal));
+    // relaxed mode: only this library's launches go into the capture, and a cudaFree / cudaMalloc issued meanwhile by the same thread
+    // (a garbage-collected engine being destroyed in a Python host, an allocator) must not invalidate it
+    CUDA_TRY(cudaStreamBeginCapture((cudaStream_t) stream, cudaStreamCaptureModeRelaxed));
     h->capturing = true;
     h->capture_phase0 = h->phase;
     h->capture_steps = 0;

@@ -74,6 +74,7 @@ def run_oracle(syn, integ, precision, steps, pool=None):
 
 
 def run_gpu(syn, integ, precision, steps, pool=None, mode="fused", graph=0):
+    run_gpu.last_error = ""
     names = {L.SINGLE: "single", L.MIXED: "mixed", L.DOUBLE: "double"}
     hb = H.make_host_buffers(precision, syn.positions, syn.velocities, syn.masses)
     if pool is None:
@@ -89,4 +90,5 @@ def run_gpu(syn, integ, precision, steps, pool=None, mode="fused", graph=0):
         rc = 0
     except s2.Seekr2Error as e:
         rc = e.code
+        run_gpu.last_error = str(e)                          # shown by the callers' assertion messages
     return rc, ctx, H.download(ctx)

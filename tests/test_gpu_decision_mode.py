@@ -161,6 +161,7 @@ KNOB_SETS = [
     # the one-pair fast path of the packed slot warp (default here: difference of the centroid sums reduced directly, activity read
     # off a comparison): off, and with the general term evaluation
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PAIR_FAST": "0"},
+    {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PAIR_FAST": "0", "SEEKR2_B200_PACKED": "0"},               # general sums, aligned layout
     {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_PAIR_FAST": "1", "SEEKR2_B200_LOCAL_THREADS": "160"},
 ]
 

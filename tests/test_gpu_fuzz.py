@@ -196,7 +196,7 @@ def test_random_elber_cases_match_the_oracle(cuda_device, seed):
         except s2.Seekr2Error as e:                     # more than 256 padded slots: LOCAL is refused, the hand-off covers it
             assert decision == "local" and "group slots" in str(e)
             continue
-        assert rc == grc == 0, (seed, mode, decision)
+        assert rc == grc == 0, (seed, mode, decision, S.run_gpu.last_error)
         assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (seed, mode, decision)
         H.assert_state_equal(ob, gb, n, f"elber seed {seed} {mode} {decision}")
         so, sg = o.state(), integ.getAnchorState(0)
