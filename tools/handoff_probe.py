@@ -11,6 +11,11 @@ from helpers import L, s2
 A = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 NATOMS = int(sys.argv[2]) if len(sys.argv) > 2 else bench.N_ATOMS
 syn, positions, forces, _ = bench.build_workload(A, NATOMS, 1)
+if os.environ.get("PROBE_HG"):      # the bench's host-guest leg: 2 520 atoms, 147 + 15 atom groups (aligned slot layout)
+    host, guest = list(range(0, 147)), list(range(147, 162))
+    syn = H.pair_sphere_system(2520, host, guest, 0.3, 0.5, 3, dt=0.002, tether_k=0.0)
+    H.place_pair_distance(syn, host, guest, 0.4)
+    positions = syn.positions
 integ = H.make_mmvt_integrator(syn, "")
 if os.environ.get("PROBE_GRAPH"): integ.setUseGraph(True, 32)
 if len(sys.argv) > 3: integ.setDecisionMode(sys.argv[3])
@@ -39,7 +44,7 @@ for it in range(3):
         for who, off, stages in (("block 0, slot thread 0 (leader)", 0, slot), ("last block, streaming thread T/2", 16, strm)):
             c = p[8 * A + 4 + off: 8 * A + 4 + off + 11]
             print(f"   LOCAL mode, {who}, SM cycles since block start: " + "; ".join(f"{n} {int(c[i + 1] - c[0])}" for i, n in enumerate(stages) if c[i + 1] > 0)
-                  + (f"; [loads returned {int(c[8] - c[0])}]" if c[8] > 0 else ""))
+                  + (f"; [loads returned {int(c[8] - c[0])}]" if c[8] > 0 else "") + (f"; [prologue done, before the wait {int(c[9] - c[0])}]" if c[9] > 0 else ""))
         continue
     stages = ["step index loaded", "gathers issued", "gathers back", "cleared+sync", "advanced", "accumulated", "all warps reduced",
               "boundary terms", "published", "bookkeeping+slab+clock"]
