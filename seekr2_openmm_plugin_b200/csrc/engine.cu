@@ -478,6 +478,18 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         const bool latency = stream_blocks <= (long long) prop.multiProcessorCount * kLocalLatencyBlocksPerSm;
         h->local_regs = latency ? kLocalRegsLatency : cfg->kind == SEEKR2_B200_KIND_LANGEVIN ? kLocalRegsPlain : kLocalRegsThroughput;
         if (stream_blocks <= (long long) prop.multiProcessorCount * kLocalSmallBlockBlocksPerSm) local_threads = 128;   // also the latency regime: host-guest size 2.51 vs 2.70 us (plain 1.48 vs 1.69), one trypsin anchor 2.27 vs 2.27 (plain 1.73 vs 1.85)
+        if (cfg->kind == SEEKR2_B200_KIND_LANGEVIN && !latency) {
+            // plain Langevin, multi-tile regime: 48 registers (more resident blocks) or the 64 ptxas takes under the 72 cap -- whichever
+            // wastes fewer block slots in the last round of tiles (rounds x resident blocks; 12 anchors: 2 x 1480 against 2 x 1184,
+            // measured 5.1 against 4.7 us; 8 anchors: 1 x 1480 against 2 x 1184, 3.2 against 3.9)
+            const long long tiles = (long long) A * ((cfg->num_atoms + local_threads - 1) / local_threads);
+            auto padded_work = [&](int regs) {
+                const long long per_sm = std::min<long long>(65536 / ((long long) regs * local_threads), 2048 / local_threads);
+                const long long resident = per_sm * prop.multiProcessorCount;
+                return ((tiles + resident - 1) / resident) * resident;
+            };
+            h->local_regs = padded_work(kLocalRegsPlain) <= padded_work(64) ? kLocalRegsPlain : kLocalRegsThroughput;
+        }
         {   // one or two anchors of a large system: 192-thread tiles fill the GPU with one or two blocks per SM -- fewer, evenly spread
             // blocks, and fewer slot warps asking L2 for the same lines (23 036 atoms: one anchor 1.94 vs 2.07 us, two 2.35 vs 2.61;
             // profiles/r02_local_threads_sweep.json)
