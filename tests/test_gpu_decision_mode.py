@@ -208,3 +208,31 @@ def test_kernel_knobs_do_not_change_a_bit(cuda_device, monkeypatch, kind, middle
         assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3], env
         for a in range(A):
             H.assert_state_equal(ref[0][a], got[0][a], n, f"{env}, anchor {a}")
+
+
+@pytest.mark.parametrize("groups", [(11, 9), (40, 9)])        # packed slot layout (one warp) / aligned layout (whole warps per group)
+@pytest.mark.parametrize("offset_nm", [0.0, 700.0, 6000.0])
+def test_one_pair_fast_path_and_its_fallback_match_the_oracle(cuda_device, groups, offset_nm):
+    """The LOCAL kernel's one-pair fast path sums the DIFFERENCE of the two centroid sums and needs every fixed-point term below
+    2^47 (packed) / 2^45 (aligned); a system far from the origin exceeds that and must take the general path.  The boundary depends
+    on the difference of two centroids only, so the same run translated by 0, 700 and 6 000 nm (|w x| 2^40 up to 2^48.6 for the
+    smaller group) is checked against the oracle bit for bit, in mixed and double precision: state, records, statistics."""
+    import scenarios as S
+    na, nb = groups
+    host, guest = list(range(0, na)), list(range(na, na + nb))
+    for precision in (L.MIXED, L.DOUBLE):
+        syn = H.pair_sphere_system(700, host, guest, 0.198, 0.202, H.SEED_BASE + 71, tether_k=0.0)
+        H.place_pair_distance(syn, host, guest, 0.20)
+        syn.positions = syn.positions + np.array([offset_nm, -0.5 * offset_nm, 0.25 * offset_nm])
+        steps = 240
+        pool = H.gaussian_pool(H.SEED_BASE + 72, steps * ((700 + 31) // 32 * 32))
+        rc, o, ob = S.run_oracle(syn, H.make_mmvt_integrator(syn, ""), precision, steps, pool)
+        integ = H.make_mmvt_integrator(syn, "")
+        integ.setDecisionMode("local")
+        grc, ctx, gb = S.run_gpu(syn, integ, precision, steps, pool, mode="fused", graph=8)
+        assert rc == grc == 0, (groups, offset_nm, precision, S.run_gpu.last_error)
+        assert H.records_as_tuples(o.records()) == H.records_as_tuples(integ.getRecords(0)), (groups, offset_nm, precision)
+        H.assert_state_equal(ob, gb, 700, f"groups {groups}, offset {offset_nm} nm, precision {precision}")
+        assert H.stats_tuple(o.state(), 2) == H.stats_tuple(integ.getAnchorState(0), 2)
+        if offset_nm == 0.0:
+            assert len(o.records()) > 0, "the run must bounce"
