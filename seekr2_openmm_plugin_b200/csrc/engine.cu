@@ -246,7 +246,10 @@ template <int P, int KIND, int SCHEME, int REGS> int launch_local(seekr2_b200_en
                 CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
                 const size_t max_dyn = (size_t) optin > fa.sharedSizeBytes ? (size_t) optin - fa.sharedSizeBytes : 0;
                 while (U > 0 && (size_t) U * per_tile > max_dyn) U--;
-                if (U > 0) CUDA_TRY(cudaFuncSetAttribute(fused_local_kernel<P, KIND, SCHEME, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) U * per_tile)));
+                // the attribute belongs to the function, not to this engine: only ever raise it (another engine of the process may be
+                // launching the same instantiation with a larger log)
+                if (U > 0 && (size_t) U * per_tile > (size_t) fa.maxDynamicSharedSizeBytes)
+                    CUDA_TRY(cudaFuncSetAttribute(fused_local_kernel<P, KIND, SCHEME, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) U * per_tile)));
                 for (; U > 0; U--) {
                     int occ = 0;
                     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_local_kernel<P, KIND, SCHEME, REGS>, (int) threads, (size_t) U * per_tile));

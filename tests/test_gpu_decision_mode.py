@@ -236,3 +236,38 @@ def test_one_pair_fast_path_and_its_fallback_match_the_oracle(cuda_device, group
         assert H.stats_tuple(o.state(), 2) == H.stats_tuple(integ.getAnchorState(0), 2)
         if offset_nm == 0.0:
             assert len(o.records()) > 0, "the run must bounce"
+
+
+def test_two_engines_with_different_undo_logs_share_the_kernel(cuda_device, monkeypatch):
+    """The dynamic shared memory limit of the LOCAL kernel is an attribute of the FUNCTION: an engine that sizes a small undo log
+    must not lower it under an engine of the same process that launches the same instantiation with a large one."""
+    A, n = 4, 3000
+
+    def make(env):
+        for k in ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_LOCAL_UNDO_TILES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        syn, positions = _shell_workload(A, n, H.SEED_BASE + 65)
+        integ = H.make_mmvt_integrator(syn, "")
+        integ.setRandomNumberSeed(13)
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": "mixed"}, numAnchors=A)
+        ctx.setPositions(positions)
+        ctx.setVelocities(syn.velocities)
+        integ.step(8)                                          # the first launch sizes the grid and the log
+        return ctx, integ
+
+    big = {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": "99"}   # 144 KB
+    small = {"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": "1"}  # 3 KB
+    ctx_ref, integ_ref = make(big)
+    integ_ref.step(392)
+    ctx_a, integ_a = make(big)
+    ctx_b, integ_b = make(small)
+    for _ in range(49):
+        integ_a.step(8)
+        integ_b.step(8)
+    assert sum(len(integ_ref.getRecords(a)) for a in range(A)) >= 4, "the run must bounce"
+    for a in range(A):
+        H.assert_state_equal(H.download(ctx_ref, a), H.download(ctx_a, a), n, f"large log, anchor {a}")
+        H.assert_state_equal(H.download(ctx_ref, a), H.download(ctx_b, a), n, f"small log, anchor {a}")
+        assert H.records_as_tuples(integ_ref.getRecords(a)) == H.records_as_tuples(integ_a.getRecords(a)) == H.records_as_tuples(integ_b.getRecords(a))
