@@ -271,3 +271,37 @@ def test_two_engines_with_different_undo_logs_share_the_kernel(cuda_device, monk
         H.assert_state_equal(H.download(ctx_ref, a), H.download(ctx_a, a), n, f"large log, anchor {a}")
         H.assert_state_equal(H.download(ctx_ref, a), H.download(ctx_b, a), n, f"small log, anchor {a}")
         assert H.records_as_tuples(integ_ref.getRecords(a)) == H.records_as_tuples(integ_a.getRecords(a)) == H.records_as_tuples(integ_b.getRecords(a))
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("middle", [False, True])
+def test_undo_log_in_single_and_double_precision(cuda_device, monkeypatch, precision, middle):
+    """The undo log's entry is (real4, mixed4) of the precision mode -- 32 B per atom in single, 64 B in double precision.  Blocks of
+    64 streaming threads walking all 47 tiles of their anchor with two of them logged (then one tile behind the decision barrier,
+    then predicated stores), against the default hand-off kernel: atoms, records, statistics, clock, with bounces."""
+    A, n = 4, 3000
+    keys = ("SEEKR2_B200_DECIDE", "SEEKR2_B200_LOCAL_THREADS", "SEEKR2_B200_LOCAL_RESIDENT", "SEEKR2_B200_LOCAL_UNDO_TILES")
+
+    def run(env):
+        for k in keys:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        syn, positions = _shell_workload(A, n, H.SEED_BASE + 67)
+        integ = H.make_mmvt_integrator(syn, "", middle=middle)
+        integ.setRandomNumberSeed(17)
+        integ.setUseGraph(True, 8)
+        ctx = s2.Context(syn.system, integ, {"CudaPrecision": precision}, numAnchors=A)
+        ctx.setPositions(positions)
+        ctx.setVelocities(syn.velocities)
+        integ.step(400)
+        return ([H.download(ctx, a) for a in range(A)], [H.records_as_tuples(integ.getRecords(a)) for a in range(A)],
+                [H.stats_tuple(integ.getAnchorState(a), 2) for a in range(A)])
+
+    ref = run({"SEEKR2_B200_DECIDE": "h"})
+    assert sum(len(r) for r in ref[1]) >= 4, "the run must bounce"
+    for tiles in ("2", "99"):
+        got = run({"SEEKR2_B200_DECIDE": "l", "SEEKR2_B200_LOCAL_THREADS": "64", "SEEKR2_B200_LOCAL_RESIDENT": "6", "SEEKR2_B200_LOCAL_UNDO_TILES": tiles})
+        assert got[1] == ref[1] and got[2] == ref[2], (precision, middle, tiles)
+        for a in range(A):
+            H.assert_state_equal(ref[0][a], got[0][a], n, f"{precision}, middle={middle}, {tiles} logged tiles, anchor {a}")
