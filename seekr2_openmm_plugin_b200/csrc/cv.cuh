@@ -73,6 +73,8 @@ struct EngineDev {
     int group_slot_begin[SEEKR2_B200_MAX_GROUPS];   // first slot of group g and the number of its REAL slots (padding excluded):
     int group_slot_count[SEEKR2_B200_MAX_GROUPS];   // FLAG_CV_FLOAT sums a group's float terms sequentially in this order
     unsigned spin_limit;         // polls (64 ns apart) after which a block waiting for an in-launch decision traps (0xffffffff = never)
+    int late_step;               // 1: this launch follows seekr2_b200_resync under programmatic dependent launch -- the step-index shadow is
+                                 // read AFTER griddepcontrol.wait (the resync kernel has just written it); only with a Gaussian pool
     int tune;                    // A/B knobs (SEEKR2_B200_TUNE): bit 5 the LOCAL kernel's slot warp joins the undo barrier on bounce steps only
 };
 constexpr int kLayoutAligned = 0, kLayoutPacked = 1;

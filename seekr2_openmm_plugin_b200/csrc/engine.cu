@@ -86,6 +86,9 @@ struct seekr2_b200_engine {
     int sm_count = 0;
     bool plain_next = true;         // the next fused launch is an ordinary one (no programmatic dependent launch): set whenever the step-index
                                     // shadow was (re)written by something other than the fused launch two steps back
+    bool late_step_allowed = true;  // SEEKR2_B200_LATE_STEP=0: off (A/B knob)
+    bool plain_by_resync = false;   // ... and that something was seekr2_b200_resync: with a Gaussian pool the fused launch may still overlap it
+                                    // (programmatic dependent launch, step index read after the wait: dev.late_step)
     bool shadow_stale = false;      // two-pass steps advanced the clock but not the step-index shadow
     int finish_parity = 0;          // half of decision[2][A] the next finish launch publishes in (the other half is cleared by it)
     std::vector<int> group_atom_of_slot;   // slot -> atom index as given at create (seekr2_b200_set_atom_order maps it through the caller's order)
@@ -501,6 +504,7 @@ int seekr2_b200_create(const seekr2_b200_config* cfg, seekr2_b200_handle* out) {
         }
         if (const char* lr = getenv("SEEKR2_B200_LOCAL_REGS")) h->local_regs = atoi(lr) == kLocalRegsThroughput ? kLocalRegsThroughput : atoi(lr) == kLocalRegsPlain ? kLocalRegsPlain : kLocalRegsLatency;   // A/B knob (48: plain Langevin only)
         if (const char* pd = getenv("SEEKR2_B200_PDL")) if (pd[0] == '0') h->use_pdl = false;                       // A/B knob
+        if (const char* lt = getenv("SEEKR2_B200_LATE_STEP")) if (lt[0] == '0') h->late_step_allowed = false;       // A/B knob
     }
 
     // Group slots.  ALIGNED layout (hand-off kernel; LOCAL with larger groups): every group's slot range is rounded up to a
@@ -725,6 +729,7 @@ int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* buf
         h->slab_valid = true;
         h->shadow_stale = false;     // launch_gather ends with refresh_shadow_kernel
         h->plain_next = true;        // ... an ordinary launch: the next fused launch must not read the shadow before it has completed
+        h->plain_by_resync = false;
     }
     return rc;
 }
@@ -738,7 +743,8 @@ int seekr2_b200_resync(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, vo
     if (rc == SEEKR2_B200_OK) {
         h->slab_valid = true;
         h->shadow_stale = false;
-        h->plain_next = true;        // the shadow was written by an ordinary launch: the next fused launch must not read it early
+        h->plain_next = true;        // the shadow was written by an ordinary launch: the next fused launch must not read it early ...
+        h->plain_by_resync = true;   // ... unless it reads it late (pool mode)
     }
     return rc;
 }
@@ -803,13 +809,19 @@ int seekr2_b200_step(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, uint
         CUDA_TRY(cudaGetLastError());
         h->shadow_stale = false;
         h->plain_next = true;
+        h->plain_by_resync = false;
     }
+    // directly behind seekr2_b200_resync, with a Gaussian pool: overlap the resync kernel (it releases its dependents at once)
+    h->dev.late_step = h->use_pdl && h->late_step_allowed && h->plain_next && h->plain_by_resync && bufs->d_random != nullptr && !h->capturing ? 1 : 0;
+    if (h->dev.late_step) h->plain_next = false;
     int rc = DISPATCH_PRECISION(h, launch_fused_kind<SINGLE>(h, bufs, random_index, s),
                                 launch_fused_kind<MIXED>(h, bufs, random_index, s),
                                 launch_fused_kind<DOUBLE>(h, bufs, random_index, s));
     if (rc != SEEKR2_B200_OK) return rc;
+    h->dev.late_step = 0;
     h->phase = (h->phase + 1) & 3;   // slab half and decision flag alternate every launch; the step-index slots cycle through four
     h->plain_next = false;
+    h->plain_by_resync = false;
     if (h->capturing) h->capture_steps++;
     return SEEKR2_B200_OK;
 }
@@ -864,6 +876,7 @@ int seekr2_b200_graph_begin(seekr2_b200_handle h, void* stream) {
     h->capture_finish_parity0 = h->finish_parity;
     h->capture_plain0 = h->plain_next;
     h->plain_next = true;            // the graph's first step has no kernel of this graph in front of it
+    h->plain_by_resync = false;
     return SEEKR2_B200_OK;
 }
 
@@ -983,6 +996,7 @@ int seekr2_b200_set_time(seekr2_b200_handle h, int32_t anchor, double time, int6
     set_time_kernel<<<1, 1, 0, (cudaStream_t) stream>>>(h->dev, anchor, time, (long long) step_count, h->phase);
     CUDA_TRY(cudaGetLastError());
     h->plain_next = true;            // the step-index shadow was written by an ordinary launch
+    h->plain_by_resync = false;
     return SEEKR2_B200_OK;
 }
 
