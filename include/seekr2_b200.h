@@ -283,7 +283,9 @@ int seekr2_b200_sync_groups(seekr2_b200_handle h, const seekr2_b200_buffers* buf
    CMMotionRemover, atom reordering -- the reference is immune because it re-reads everything every step,
    CudaSeekr2Kernels.cpp:214-246): ONE small launch that re-gathers the boundary-group atoms into the slab and takes the
    step index from the anchor clock.  Queue it in front of every fused step; the pair is still a single pass over the
-   atoms (no posDelta round trip).  Not needed between back-to-back fused steps of a caller that owns the buffers.   */
+   atoms (no posDelta round trip).  Not needed between back-to-back fused steps of a caller that owns the buffers.
+   When the step that follows draws its normals from a Gaussian pool (bufs->d_random != NULL, OpenMM's convention), it is
+   launched as a programmatic dependent of this kernel and overlaps it (it reads slab and step index behind its own wait). */
 int seekr2_b200_resync(seekr2_b200_handle h, const seekr2_b200_buffers* bufs, void* stream);
 
 /* OpenMM's CUDA platform reorders atoms now and then (cu.reorderAtoms(), CudaSeekr2Kernels.cpp:365): the buffers then

@@ -207,12 +207,14 @@ def test_poll_reports_appended_records_without_a_cuda_call(cuda_device):
     assert pending.value == 0
 
 
+@pytest.mark.parametrize("decision", ["local", "handoff"])
 @pytest.mark.parametrize("precision", [L.SINGLE, L.MIXED, L.DOUBLE])
-def test_resync_every_step_and_permuted_atom_order(cuda_device, precision):
+def test_resync_every_step_and_permuted_atom_order(cuda_device, precision, decision):
     """What the OpenMM adapter does: seekr2_b200_resync in front of every fused step (the slab is re-read from the caller's
     buffers), and seekr2_b200_set_atom_order when the caller's buffers hold the atoms in another order.  The same system
     with its atoms stored in reversed order must evolve identically (in-kernel normals are keyed by buffer index, so an
-    injected pool, permuted alike, is used)."""
+    injected pool, permuted alike, is used).  With a pool the fused step is launched as a programmatic dependent of the
+    resync kernel and reads slab and step index behind its wait (late_step), in both fused kernels."""
     host, guest = list(range(0, 11)), list(range(11, 20))
     n = 300
     syn = H.pair_sphere_system(n, host, guest, 0.185, 0.195, H.SEED_BASE + 21, tether_k=0.0)
@@ -226,6 +228,7 @@ def test_resync_every_step_and_permuted_atom_order(cuda_device, precision):
 
     def run(order):
         integ = H.make_mmvt_integrator(syn, "")
+        integ.setDecisionMode(decision)
         names = {L.SINGLE: "single", L.MIXED: "mixed", L.DOUBLE: "double"}
         hb = H.make_host_buffers(precision, syn.positions, syn.velocities, syn.masses)
         perm = np.arange(npad)
