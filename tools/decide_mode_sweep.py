@@ -15,7 +15,14 @@ STEPS, G = int(os.environ.get("SWEEP_STEPS", "4096")), bench.STEPS_PER_GRAPH
 
 def us_per_step(A, kind, mode):
     syn, positions, forces, _ = bench.build_workload(A, NATOMS, 0x5EEC2004)
-    integ = H.make_mmvt_integrator(syn, "") if kind == "mmvt" else s2.LangevinIntegrator(300.0, 1.0, bench.DT_PS)
+    if kind == "mmvt":
+        integ = H.make_mmvt_integrator(syn, "")
+    elif kind == "elber":                                    # slot role in the anchor's first block only, no undo log, never bounces
+        integ = s2.ElberLangevinIntegrator(300.0, 1.0, bench.DT_PS, "")
+        integ.addSrcMilestoneGroup(1)
+        integ.setEndOnSrcMilestone(False)
+    else:
+        integ = s2.LangevinIntegrator(300.0, 1.0, bench.DT_PS)
     integ.setRandomNumberSeed(7)
     integ.setDecisionMode(mode)
     integ.ringCapacity = 1 << 14
@@ -40,16 +47,21 @@ def us_per_step(A, kind, mode):
     return best, integ.getDecisionMode()
 
 
+KINDS = os.environ.get("SWEEP_KINDS", "mmvt,langevin").split(",")
 out = {"atoms": NATOMS, "steps": STEPS, "steps_per_graph": G, "rows": []}
 for A in [int(a) for a in os.environ.get("SWEEP_ANCHORS", "1,2,4,6,8,12,16,24,32,48,64,96,128").split(",")]:
     row = {"anchors": A}
-    for kind in ("mmvt", "langevin"):
+    for kind in KINDS:
         for mode in os.environ.get("SWEEP_MODES", "auto,local,handoff").split(","):
             t, chosen = us_per_step(A, kind, mode)
             row[f"{kind}_{mode}_us"] = round(t, 3)
             if mode == "auto" and kind == "mmvt":
                 row["auto_mode"] = chosen
     modes = os.environ.get("SWEEP_MODES", "auto,local,handoff").split(",")
+    if "langevin" not in KINDS or "mmvt" not in KINDS:
+        out["rows"].append(row)
+        print(json.dumps(row), file=sys.stderr, flush=True)
+        continue
     plain = min(row[f"langevin_{m}_us"] for m in modes)      # the fastest plain Langevin step, whatever launch shape
     for m in modes:
         row[f"mmvt_over_plain_{m}"] = round(row[f"mmvt_{m}_us"] / plain, 3)
