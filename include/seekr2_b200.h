@@ -430,6 +430,10 @@ int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t p
                                   int64_t anchor_stride, int32_t num_steps, uint64_t seed,
                                   uint32_t anchor_base, uint32_t anchor_id_stride, uint64_t step0, void* stream);
 
+/* test hook of the in-kernel generator: *d_mismatches = the number of float bit patterns (of all 2^32) on which the call-free
+   square root the Box-Muller step uses (kernels.cuh, sqrt_no_call) differs from sqrtf; must be 0                              */
+int seekr2_b200_harness_check_sqrt(unsigned long long* d_mismatches, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,6 +135,7 @@ SYMBOLS = {
     "seekr2_b200_harness_tether_force": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_double, _P, _P]),
     "seekr2_b200_harness_bond_force": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "seekr2_b200_harness_fill_pool": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, _P]),
+    "seekr2_b200_harness_check_sqrt": (C.c_int, [_P, _P]),
     "seekr2_b200_set_rng": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32]),
     "seekr2_b200_debug_set_probe": (C.c_int, [_P, _P]),
 }

@@ -1154,4 +1154,13 @@ int seekr2_b200_harness_fill_pool(void* d_random, int32_t num_anchors, int32_t p
     return SEEKR2_B200_OK;
 }
 
+int seekr2_b200_harness_check_sqrt(unsigned long long* d_mismatches, void* stream) {
+    if (!d_mismatches) return fail(SEEKR2_B200_ERR_INVALID, "bad argument");
+    static_assert(kThreads == 256, "2^32 patterns = 65536 blocks x 256 rounds x 256 threads");
+    CUDA_TRY(cudaMemsetAsync(d_mismatches, 0, sizeof(unsigned long long), (cudaStream_t) stream));
+    check_sqrt_kernel<<<65536, kThreads, 0, (cudaStream_t) stream>>>(d_mismatches);
+    CUDA_TRY(cudaGetLastError());
+    return SEEKR2_B200_OK;
+}
+
 }  // extern "C"
