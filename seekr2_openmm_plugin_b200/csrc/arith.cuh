@@ -135,9 +135,14 @@ template <> __device__ __forceinline__ float  from_ll<float>(long long v)  { ret
 template <> __device__ __forceinline__ double from_ll<double>(long long v) { return __ll2double_rn(v); }
 
 // SQRT of the OpenMM prelude: sqrtf unless full double precision (langevin.cu:22)
+__device__ __forceinline__ float sqrt_no_call(float x);   // kernels.cuh
 template <int P> __device__ __forceinline__ typename Prec<P>::mixed sqrt_inv_mass(typename Prec<P>::mixed w) {
     if constexpr (P == DOUBLE) return __dsqrt_rn(w);
+#ifdef SEEKR2_SQRT_INV_MASS_NO_CALL                              // experimental builds: the call-free square root here too (bit-identical)
+    else return (typename Prec<P>::mixed) sqrt_no_call((float) w);
+#else
     else return (typename Prec<P>::mixed) __fsqrt_rn((float) w);
+#endif
 }
 
 // parameters of one step, prepared on the host in the precision the reference kernel computes in
